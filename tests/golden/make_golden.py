@@ -1,0 +1,298 @@
+"""Generate the golden vectors in tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container only (it needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports /root/reference/model.py as is, feeds it materialised inputs (the reference seeds
+nothing on CPU) and stores inputs + dense-reference outputs restricted to the
+places the training script reads them: CSR entries of adj_sym and explicit pair lists.  Every
+fixture holds
+    N K d beta T, src/dst (train edge columns, directed, as main_disentangled.py:136),
+    Z [N,K,d]                      factor embeddings entering Disentangle_layer (model.py:106)
+    ref_rows/ref_cols              adj_sym.nonzero() (main_disentangled.py:141-142)
+    ref_kstar/ref_w/ref_att/ref_s  routing, softmax prob, att value (model.py:61-74), row sums
+    ref_margin                     top1-top2 softmax margin per entry (near-tie diagnostics)
+    ref_H [N,K*d]                  first return of Disentangle.forward (model.py:114)
+    pu/pv, ref_prob                pair list and link_pred[pu,pv] (model.py:113)
+    loss pair lists, ref_loss, ref_dZ   loss of main_disentangled.py:195 and dL/dZ by autograd
+The reference is driven through its own Disentangle.forward: the K factor MLPs are swapped for
+modules that return a leaf tensor, so Z is an input we control and autograd gives dL/dZ.
+"""
+import os
+import pickle
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REF = "/root/reference"
+sys.path.insert(0, REF)
+import model as refmodel  # noqa: E402  (the reference, unchanged)
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+torch.set_num_threads(8)
+
+
+class _Leaf(nn.Module):
+    def __init__(self, z):
+        super().__init__()
+        self.z = nn.Parameter(z.clone())
+
+    def forward(self, x):
+        return self.z
+
+
+def dense_adj_sym(src, dst, n):
+    """main_disentangled.py:138-142"""
+    ei = torch.stack([torch.as_tensor(src), torch.as_tensor(dst)])
+    adj = torch.sparse_coo_tensor(ei, torch.ones(ei.shape[1]), torch.Size([n, n])).to_dense()
+    adj[adj != 0] = 1
+    adj_sym = adj + adj.t()
+    adj_sym[adj_sym != 0] = 1
+    return adj_sym
+
+
+def dense_mask(u, v, n):
+    """main_disentangled.py:167-178 (duplicates SUM)"""
+    ei = torch.stack([torch.as_tensor(u), torch.as_tensor(v)])
+    return torch.sparse_coo_tensor(ei, torch.ones(ei.shape[1]), torch.Size([n, n])).to_dense()
+
+
+def structured_negatives(src, dst, n, rng):
+    """PyG structured_negative_sampling restated ([external]): for every
+    edge column (i,j) draw k uniformly until (i,k) is not an edge."""
+    pos = set((src * n + dst).tolist())
+    k = rng.integers(0, n, size=src.size)
+    bad = np.array([(int(a) * n + int(b)) in pos for a, b in zip(src, k)])
+    while bad.any():
+        k[bad] = rng.integers(0, n, size=int(bad.sum()))
+        bad = np.array([(int(a) * n + int(b)) in pos for a, b in zip(src, k)])
+    return k
+
+
+def run_reference(name, src, dst, n, Z, beta, T, pu, pv, loss_pos=None, loss_neg=None, m=1,
+                  extra=None):
+    K, d = Z.shape[1], Z.shape[2]
+    model = refmodel.Disentangle(4, 8, d, nfactor=K, beta=beta, t=T)
+    leaves = [_Leaf(torch.from_numpy(Z[:, k, :].copy())) for k in range(K)]
+    model.factors = leaves
+    for i, f in enumerate(leaves):
+        model.add_module("factor_{}".format(i), f)
+    adj_sym = dense_adj_sym(src, dst, n)
+    x = torch.zeros(n, 4)
+    H, link_pred = model(x, adj_sym)
+
+    # internals of Disentangle_layer, from its own returns (model.py:77)
+    with torch.no_grad():
+        Zl = [f.z for f in leaves]
+        h_list, alpha0, att = model.disentangle_layer1(Zl, adj_sym)
+        alpha = alpha0 / torch.sum(alpha0, dim=0)
+        rows, cols = adj_sym.nonzero(as_tuple=True)
+        p = torch.argmax(alpha, dim=0)
+        kstar = p[rows, cols]
+        w = alpha[kstar, rows, cols]
+        att_st = torch.stack(att, 0)
+        att_e = att_st[kstar, rows, cols]
+        # the att list is zero off the routed factor
+        chk = att_st[:, rows, cols].clone()
+        chk[kstar, torch.arange(rows.numel())] = 0
+        assert float(chk.abs().max()) == 0.0 if rows.numel() else True
+        s = torch.zeros(n, K)
+        for k in range(K):
+            mk = (kstar == k)
+            s[:, k].index_add_(0, rows[mk], w[mk])
+        s[s == 0] = 1
+        top2 = torch.topk(alpha[:, rows, cols], min(2, K), dim=0).values
+        margin = (top2[0] - top2[1]) if K > 1 else torch.ones(rows.numel())
+
+    out = dict(N=n, K=K, d=d, beta=np.float64(beta), T=np.float64(T),
+               src=np.asarray(src, np.int64), dst=np.asarray(dst, np.int64), Z=Z,
+               ref_rows=rows.numpy(), ref_cols=cols.numpy(), ref_kstar=kstar.numpy().astype(np.uint8),
+               ref_w=w.numpy(), ref_att=att_e.numpy(), ref_s=s.numpy(), ref_margin=margin.numpy(),
+               ref_H=H.detach().numpy(), pu=np.asarray(pu, np.int64), pv=np.asarray(pv, np.int64),
+               ref_prob=link_pred[torch.as_tensor(pu), torch.as_tensor(pv)].detach().numpy())
+    if loss_pos is not None:
+        ori = torch.ones(n, n)  # labels: the script reads ori_adj (1 on positives, 0 on negatives)
+        pos_adj = dense_mask(loss_pos[0], loss_pos[1], n)
+        neg_adj = dense_mask(loss_neg[0], loss_neg[1], n)
+        # main_disentangled.py:195
+        loss = F.binary_cross_entropy(link_pred[pos_adj == 1].unsqueeze(0),
+                                      ori[pos_adj == 1].unsqueeze(0)) + \
+            F.binary_cross_entropy(link_pred[neg_adj == 1].unsqueeze(0),
+                                   torch.zeros_like(ori[neg_adj == 1]).unsqueeze(0)) / m
+        loss.backward()
+        dZ = torch.stack([f.z.grad for f in leaves], dim=1)
+        out.update(loss_pos_u=np.asarray(loss_pos[0], np.int64), loss_pos_v=np.asarray(loss_pos[1], np.int64),
+                   loss_neg_u=np.asarray(loss_neg[0], np.int64), loss_neg_v=np.asarray(loss_neg[1], np.int64),
+                   m=m, ref_loss=np.float64(loss.item()), ref_dZ=dZ.numpy())
+    if extra:
+        out.update(extra)
+    if n <= 64:
+        out["ref_link_pred"] = link_pred.detach().numpy()
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: N={n} K={K} d={d} nnz={rows.numel()} min_margin={float(margin.min()) if margin.numel() else float("nan"):.3e} "
+          f"-> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+# ------------------------------------------------------------------------------------------
+def tiny_cases():
+    rng = np.random.default_rng(7)
+    # (a) generic: self loops, duplicates, isolated nodes, a hub
+    n, K, d = 40, 3, 8
+    src = rng.integers(0, n - 4, size=90)      # nodes n-4.. isolated
+    dst = rng.integers(0, n - 4, size=90)
+    src = np.concatenate([src, src[:10], [3, 5, 7], np.full(30, 2)])        # duplicates, self loops, hub
+    dst = np.concatenate([dst, dst[:10], [3, 5, 7], np.arange(30) % (n - 4)])
+    Z = (rng.standard_normal((n, K, d)) * 0.6).astype(np.float32)
+    pu = rng.integers(0, n, size=200)
+    pv = rng.integers(0, n, size=200)
+    pu[:5] = pv[:5]                                                         # (u,u) pairs
+    lp = (np.concatenate([src[:60], src[:5]]), np.concatenate([dst[:60], dst[:5]]))  # dup -> dropped
+    ln = (rng.integers(0, n, size=150), rng.integers(0, n, size=150))
+    run_reference("tiny_generic", src, dst, n, Z, beta=0.7, T=1.0, pu=pu, pv=pv,
+                  loss_pos=lp, loss_neg=ln, m=3)
+    # (b) one factor never wins (tiny embeddings) -> s == 0 -> 1 for that factor everywhere;
+    #     temperature != 1; d not a multiple of 4; K = 4
+    n, K, d = 33, 4, 6
+    src = rng.integers(0, n, size=120)
+    dst = rng.integers(0, n, size=120)
+    Z = (rng.standard_normal((n, K, d)) * 0.8).astype(np.float32)
+    Z[:, 2, :] = -np.abs(Z[:, 2, :]) * 1e-3 * np.sign(rng.standard_normal((n, 1)))
+    Z[:, 2, :] = 0.0
+    Z[:, 0, :] += 1.0                                                      # factor 0 dominates
+    pu = rng.integers(0, n, size=150)
+    pv = rng.integers(0, n, size=150)
+    run_reference("tiny_deadfactor_T2", src, dst, n, Z, beta=0.5, T=2.0, pu=pu, pv=pv,
+                  loss_pos=(src[:80], dst[:80]), loss_neg=(pu[:100], pv[:100]), m=5)
+    # (c) exact ties: factors 0 and 1 identical -> first index wins (model.py:61)
+    n, K, d = 24, 3, 4
+    src = rng.integers(0, n, size=70)
+    dst = rng.integers(0, n, size=70)
+    Z = (rng.standard_normal((n, K, d)) * 0.5).astype(np.float32)
+    Z[:, 1, :] = Z[:, 0, :]
+    pu = rng.integers(0, n, size=100)
+    pv = rng.integers(0, n, size=100)
+    run_reference("tiny_ties", src, dst, n, Z, beta=0.9, T=1.0, pu=pu, pv=pv)
+    # (d) K = 1 (softmax is 1 everywhere), wide d
+    n, K, d = 20, 1, 16
+    src = rng.integers(0, n, size=50)
+    dst = rng.integers(0, n, size=50)
+    Z = (rng.standard_normal((n, K, d)) * 0.3).astype(np.float32)
+    pu = rng.integers(0, n, size=60)
+    pv = rng.integers(0, n, size=60)
+    run_reference("tiny_K1", src, dst, n, Z, beta=0.6, T=1.0, pu=pu, pv=pv,
+                  loss_pos=(src[:30], dst[:30]), loss_neg=(pu[:40], pv[:40]), m=2)
+    # (e) empty graph: no edges at all
+    n, K, d = 12, 2, 4
+    Z = (rng.standard_normal((n, K, d)) * 0.5).astype(np.float32)
+    pu = rng.integers(0, n, size=30)
+    pv = rng.integers(0, n, size=30)
+    run_reference("tiny_empty", np.zeros(0, np.int64), np.zeros(0, np.int64), n, Z, beta=0.8, T=1.0,
+                  pu=pu, pv=pv)
+
+
+def module_case():
+    """Whole-module fixture: reference weights + x -> H, link_pred, grads of all parameters."""
+    torch.manual_seed(3)
+    rng = np.random.default_rng(11)
+    n, Fdim, nhid, d, K = 50, 12, 16, 8, 3
+    src = rng.integers(0, n, size=140)
+    dst = rng.integers(0, n, size=140)
+    model = refmodel.Disentangle(Fdim, nhid, d, nfactor=K, beta=0.7, t=1)
+    x = torch.randn(n, Fdim)
+    adj_sym = dense_adj_sym(src, dst, n)
+    H, link_pred = model(x, adj_sym)
+    pu = rng.integers(0, n, size=300)
+    pv = rng.integers(0, n, size=300)
+    lab = torch.from_numpy((rng.random(300) < 0.3).astype(np.float32))
+    loss = F.binary_cross_entropy(link_pred[torch.as_tensor(pu), torch.as_tensor(pv)], lab)
+    loss.backward()
+    out = dict(N=n, F=Fdim, nhid=nhid, d=d, K=K, beta=0.7, T=1.0, src=src, dst=dst, x=x.numpy(),
+               pu=pu, pv=pv, lab=lab.numpy(), ref_H=H.detach().numpy(),
+               ref_link_pred=link_pred.detach().numpy(), ref_loss=np.float64(loss.item()))
+    for k, v in model.state_dict().items():
+        out["sd." + k] = v.numpy()
+    for k, p in model.named_parameters():
+        out["grad." + k] = p.grad.numpy()
+    path = os.path.join(OUT, "module_small.npz")
+    np.savez_compressed(path, **out)
+    print("module_small ->", os.path.getsize(path) / 1e6, "MB")
+
+    # nhid == 1 branch: single-Linear Factor (model.py:94-95)
+    torch.manual_seed(4)
+    model = refmodel.Disentangle(Fdim, 1, d, nfactor=2, beta=0.6, t=1)
+    H, link_pred = model(x, adj_sym)
+    out = dict(N=n, F=Fdim, nhid=1, d=d, K=2, beta=0.6, T=1.0, src=src, dst=dst, x=x.numpy(),
+               ref_H=H.detach().numpy(), ref_link_pred=link_pred.detach().numpy())
+    for k, v in model.state_dict().items():
+        out["sd." + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "module_nhid1.npz"), **out)
+
+
+def load_cora():
+    """PyG-free Planetoid reader."""
+    import scipy.sparse as sp  # noqa: F401  (the pickles hold scipy matrices)
+    raw = os.path.join(REF, "data/cora/raw")
+    objs = {}
+    for nm in ("allx", "tx", "graph"):
+        with open(os.path.join(raw, "ind.cora." + nm), "rb") as f:
+            objs[nm] = pickle.load(f, encoding="latin1")
+    test_idx = np.loadtxt(os.path.join(raw, "ind.cora.test.index"), dtype=np.int64)
+    X = np.vstack([objs["allx"].toarray(), objs["tx"].toarray()]).astype(np.float32)
+    X[test_idx] = X[np.sort(test_idx)]
+    rows, cols = [], []
+    for a, nb in objs["graph"].items():
+        for b in nb:
+            if a != b:
+                rows += [a, b]
+                cols += [b, a]
+    n = X.shape[0]
+    key = np.unique(np.asarray(rows, np.int64) * n + np.asarray(cols, np.int64))
+    return X, key // n, key % n
+
+
+def real_case(name, X, src_all, dst_all, K, nhid, d, beta, seed, m=5, n_pairs=20000):
+    """The epoch body of main_disentangled.py:134-204 on materialised split + negatives."""
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    n = X.shape[0]
+    E = src_all.size
+    perm = rng.permutation(E)
+    n_tr = int(round(0.85 * E))
+    n_te = int(round((E - n_tr) * 2 / 3))
+    tr, te, va = perm[:n_tr], perm[n_tr:n_tr + n_te], perm[n_tr + n_te:]
+    # Z from the reference's own Factor2 MLPs at default init
+    mod = refmodel.Disentangle(X.shape[1], nhid, d, nfactor=K, beta=beta, t=1)
+    with torch.no_grad():
+        Z = torch.stack([f(torch.from_numpy(X)) for f in mod.factors], dim=1).numpy()
+    negs = [structured_negatives(src_all, dst_all, n, rng) for _ in range(m)]
+    neg_tr = (np.concatenate([src_all[tr]] * m), np.concatenate([k[tr] for k in negs]))
+    neg_va = (np.concatenate([src_all[va]] * m), np.concatenate([k[va] for k in negs]))
+    val_u = np.concatenate([src_all[va], neg_va[0]])
+    val_v = np.concatenate([dst_all[va], neg_va[1]])
+    pu = np.concatenate([val_u, rng.integers(0, n, size=n_pairs)])
+    pv = np.concatenate([val_v, rng.integers(0, n, size=n_pairs)])
+    run_reference(name, src_all[tr], dst_all[tr], n, Z, beta=beta, T=1.0, pu=pu, pv=pv,
+                  loss_pos=(src_all[tr], dst_all[tr]), loss_neg=neg_tr, m=m,
+                  extra=dict(n_val_pos=va.size, val_u=val_u, val_v=val_v))
+
+
+def main():
+    tiny_cases()
+    module_case()
+    cham = np.load(os.path.join(REF, "data_pre_false/chameleon/raw/chameleon.npz"))
+    X = cham["features"].astype(np.float32)
+    X = (X - X.mean(1, keepdims=True)) / X.std(1, ddof=1, keepdims=True)   # main_disentangled.py:100
+    e = cham["edges"].astype(np.int64)
+    real_case("chameleon_K5_d32", X, e[:, 0].copy(), e[:, 1].copy(), K=5, nhid=512, d=32, beta=0.7,
+              seed=0)
+    Xc, r, c = load_cora()
+    real_case("cora_K3_d32", Xc, r, c, K=3, nhid=512, d=32, beta=0.9, seed=1)   # argparse defaults
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,153 @@
+"""Pins the CPU oracle (oracle/) to the dense reference through the committed golden vectors.
+
+The fixtures were produced by tests/golden/make_golden.py from /root/reference/model.py
+(unchanged).  Tolerances: integers bit-exact; floats 1e-5 relative to the tensor's max-abs
+(BASELINE.json north_star: "within 1e-5 relative (fp32)").  Hard routing is discontinuous, so
+entries whose reference top-1/top-2 softmax margin is below 1e-5 may legitimately route
+differently under a different fp32 summation order; the test counts them, bounds their margin and
+excludes what they touch -- it never ignores a flip on a well-separated entry.
+"""
+import numpy as np
+import pytest
+
+from conftest import GRAPH_FIXTURES, load_golden
+
+RTOL = 1e-5
+TIE_MARGIN = 1e-5
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    den = max(np.abs(b).max(), 1e-30) if b.size else 1.0
+    return float(np.abs(a - b).max() / den) if b.size else 0.0
+
+
+def routed(oracle, g):
+    Z = g["Z"]
+    rowptr, col = oracle.csr_from_edges(g["src"], g["dst"], int(g["N"]))
+    H, ks, w, s = oracle.factor_fwd(rowptr, col, Z, float(g["beta"]), float(g["T"]))
+    return rowptr, col, H, ks, w, s
+
+
+@pytest.mark.parametrize("name", GRAPH_FIXTURES)
+def test_csr_equals_adj_sym_nonzero(oracle, name):
+    g = load_golden(name)
+    rowptr, col = oracle.csr_from_edges(g["src"], g["dst"], int(g["N"]))
+    assert np.array_equal(oracle.rows_of(rowptr), g["ref_rows"])
+    assert np.array_equal(col.astype(np.int64), g["ref_cols"])
+    rev = oracle.rev_index(rowptr, col)
+    rows = oracle.rows_of(rowptr)
+    assert np.array_equal(rows[rev], col.astype(np.int64))
+    assert np.array_equal(col[rev].astype(np.int64), rows)
+
+
+def flips(g, ks):
+    bad = np.nonzero(ks != g["ref_kstar"])[0]
+    assert np.all(g["ref_margin"][bad] < TIE_MARGIN), (
+        f"{bad.size} routing mismatches, worst margin {g['ref_margin'][bad].max():.3e}")
+    return bad
+
+
+@pytest.mark.parametrize("name", GRAPH_FIXTURES)
+def test_routing_and_attention(oracle, name):
+    g = load_golden(name)
+    rowptr, col, H, ks, w, s = routed(oracle, g)
+    bad = flips(g, ks)
+    ok = np.ones(ks.size, bool)
+    ok[bad] = False
+    assert relerr(w[ok], g["ref_w"][ok]) < RTOL
+    rows = oracle.rows_of(rowptr)
+    # rows with a flipped entry have a different s by construction; everything else must agree
+    clean_row = np.ones(int(g["N"]), bool)
+    clean_row[rows[bad]] = False
+    assert relerr(s[clean_row], g["ref_s"][clean_row]) < RTOL
+    att = oracle.att_values(rowptr, col, ks, w, s)
+    ok_att = ok & clean_row[col]
+    assert relerr(att[ok_att], g["ref_att"][ok_att]) < RTOL
+    # symmetry of the routing (what the atomic-free backward relies on)
+    rev = oracle.rev_index(rowptr, col)
+    assert np.array_equal(ks, ks[rev])
+    assert np.array_equal(w.view(np.uint32), w[rev].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", GRAPH_FIXTURES)
+def test_embeddings_and_scores(oracle, name):
+    g = load_golden(name)
+    N, K, d = int(g["N"]), int(g["K"]), int(g["d"])
+    rowptr, col, H, ks, w, s = routed(oracle, g)
+    bad = flips(g, ks)
+    rows = oracle.rows_of(rowptr)
+    # a flip at (i,j) changes s[i,*] hence H of i and of every neighbour of i
+    dirty = np.zeros(N, bool)
+    dirty[rows[bad]] = True
+    dirty_n = dirty.copy()
+    dirty_n[rows[dirty[col]]] = True
+    Href = g["ref_H"].reshape(N, K, d)
+    assert relerr(H[~dirty_n], Href[~dirty_n]) < RTOL
+    _, prob = oracle.pair_score_fwd(g["pu"], g["pv"], g["Z"], H, float(g["T"]))
+    okp = ~(dirty_n[g["pu"]] | dirty_n[g["pv"]])
+    assert relerr(prob[okp], g["ref_prob"][okp]) < RTOL
+    if "ref_link_pred" in g:
+        uu, vv = np.meshgrid(np.arange(N), np.arange(N), indexing="ij")
+        _, full = oracle.pair_score_fwd(uu.reshape(-1), vv.reshape(-1), g["Z"], H, float(g["T"]))
+        assert not dirty_n.any()
+        assert relerr(full.reshape(N, N), g["ref_link_pred"]) < RTOL
+
+
+def script_loss_and_grad(oracle, g, Z, H):
+    """main_disentangled.py:195 on pair lists: pairs occurring exactly once, mean BCE, neg / m."""
+    N, T = int(g["N"]), float(g["T"])
+    pu, pv = oracle.pairs_exactly_once(g["loss_pos_u"], g["loss_pos_v"], N)
+    nu, nv = oracle.pairs_exactly_once(g["loss_neg_u"], g["loss_neg_v"], N)
+    m = float(g["m"])
+    _, pp = oracle.pair_score_fwd(pu, pv, Z, H, T)
+    _, pn = oracle.pair_score_fwd(nu, nv, Z, H, T)
+    loss = oracle.bce_mean(pp, 1.0) + oracle.bce_mean(pn, 0.0) / m
+    dS = np.concatenate([oracle.bce_mean_grad_logit(pp, 1.0),
+                         oracle.bce_mean_grad_logit(pn, 0.0) / np.float32(m)]).astype(np.float32)
+    u = np.concatenate([pu, nu])
+    v = np.concatenate([pv, nv])
+    return loss, u, v, dS
+
+
+@pytest.mark.parametrize("name", [n for n in GRAPH_FIXTURES if "ref_dZ" in load_golden(n)])
+def test_loss_and_gradients(oracle, name):
+    g = load_golden(name)
+    rowptr, col, H, ks, w, s = routed(oracle, g)
+    bad = flips(g, ks)
+    loss, u, v, dS = script_loss_and_grad(oracle, g, g["Z"], H)
+    dZ_dec, dH = oracle.pair_score_bwd(u, v, g["Z"], H, dS, float(g["T"]))
+    dZ = oracle.factor_bwd(rowptr, col, g["Z"], dH, ks, w, s, float(g["beta"]), float(g["T"]),
+                           dZ_init=dZ_dec)
+    if bad.size == 0:
+        assert abs(loss - float(g["ref_loss"])) <= RTOL * abs(float(g["ref_loss"]))
+        assert relerr(dZ, g["ref_dZ"]) < 5 * RTOL
+    else:
+        # near-tie flips perturb a few rows; the bulk must still agree
+        assert abs(loss - float(g["ref_loss"])) <= 1e-3 * abs(float(g["ref_loss"]))
+        err = np.abs(dZ - g["ref_dZ"]).reshape(dZ.shape[0], -1).max(1) / np.abs(g["ref_dZ"]).max()
+        assert np.mean(err < 5 * RTOL) > 0.9
+
+
+def test_expf_accuracy(oracle):
+    x = np.concatenate([np.linspace(-87, 88, 20001), np.random.default_rng(0).normal(0, 3, 20000)])
+    x = x.astype(np.float32)
+    got = oracle.expf(x).astype(np.float64)
+    want = np.exp(x.astype(np.float64))
+    ulp = np.abs(got - want) / np.spacing(want.astype(np.float32)).astype(np.float64)
+    assert ulp.max() < 1.5
+    assert oracle.expf(np.float32(0.0)) == 1.0
+    assert np.isinf(oracle.expf(np.float32(100.0)))
+    assert oracle.expf(np.float32(-200.0)) <= 1.5e-45
+    assert np.isnan(oracle.expf(np.float32(np.nan)))
+
+
+def test_dot_is_symmetric_and_accurate(oracle):
+    rng = np.random.default_rng(1)
+    for d in (1, 3, 4, 6, 8, 12, 16, 32, 64, 100, 128):
+        x = rng.standard_normal(d).astype(np.float32)
+        y = rng.standard_normal(d).astype(np.float32)
+        a, b = oracle.dot(x, y), oracle.dot(y, x)
+        assert a.view(np.uint32) == b.view(np.uint32)
+        assert abs(float(a) - float(np.dot(x.astype(np.float64), y.astype(np.float64)))) < 1e-5 * d
