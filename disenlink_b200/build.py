@@ -1,0 +1,74 @@
+"""Builds libdisenlink_b200.so in-tree with nvcc for sm_100a (no torch headers involved).
+
+    python -m disenlink_b200.build [--force] [--verbose]
+
+The library is plain CUDA behind a C ABI (include/disenlink_b200.h); Python reaches it with ctypes.
+The .so is git-ignored but travels to the GPU box with the working tree.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ_DIR = os.path.join(HERE, "_obj")
+LIB = os.path.join(HERE, "libdisenlink_b200.so")
+SOURCES = ["graph_build.cu", "factor_fwd.cu", "factor_bwd.cu", "pair_score.cu", "dense_compat.cu"]
+HEADERS = [os.path.join(CSRC, h) for h in ("dl_common.cuh", "dl_dispatch.cuh")] + [
+    os.path.join(os.path.dirname(HERE), "include", "disenlink_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--fmad=false", "-Xptxas", "-v", "-Wno-deprecated-declarations"]
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found; libdisenlink_b200.so cannot be built")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    env = dict(os.environ)
+    # the image exports CC/CXX wrappers nvcc cannot use as host compiler; pin the system g++
+    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+
+    def compile_one(src):
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        if force or _stale(obj, [path] + HEADERS):
+            cmd = [nvcc] + ccbin + NVCC_FLAGS + ["-c", path, "-o", obj]
+            r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+            log = os.path.join(OBJ_DIR, src.replace(".cu", ".ptxas.log"))
+            with open(log, "w") as f:
+                f.write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+            if verbose:
+                print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    if force or _stale(LIB, objs):
+        cmd = [nvcc] + ccbin + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

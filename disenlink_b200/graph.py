@@ -1,0 +1,168 @@
+"""Device-resident graph handle: CSR of adj_sym plus the degree-bucketed work items.
+
+Replaces the dense [N,N] adjacency the reference builds once per run
+(main_disentangled.py:137-142) and multiplies into the routing matrix every epoch (model.py:62).
+The adjacency is constant across epochs, so the handle is built once and cached by the module.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import DlGraph, check, lib, ptr, require_cuda, stream_of
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+class Graph:
+    """CSR (rowptr int64 [N+1], col int32 [nnz]) + degree buckets + hub work items, on one GPU.
+
+    Rows are the destination nodes; ``col`` is ascending inside a row, so the entry order equals
+    ``adj_sym.nonzero()``.  ``perm`` lists rows by degree class (bit length of the degree)
+    descending; rows with degree >= 512 are "hub rows" and are cut into 512-edge segments so no
+    warp owns more than one segment.
+    """
+
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, n_nodes: int):
+        require_cuda(rowptr, "rowptr")
+        assert rowptr.dtype == torch.int64 and col.dtype == torch.int32
+        self.device = rowptr.device
+        self.N = int(n_nodes)
+        self.rowptr = rowptr.contiguous()
+        self.col = col.contiguous()
+        self.nnz = int(col.numel())
+        self._rev = None
+        self._build_items()
+
+    # ------------------------------------------------------------------ constructors
+    @classmethod
+    def from_edges(cls, src: torch.Tensor, dst: torch.Tensor, n_nodes: int) -> "Graph":
+        """Symmetrise + de-duplicate directed edge columns (self-loops kept).
+
+        [ref: main_disentangled.py:137-142]"""
+        require_cuda(src, "src")
+        dev = src.device
+        src = src.to(torch.int64).contiguous()
+        dst = dst.to(torch.int64).contiguous()
+        E = int(src.numel())
+        N = int(n_nodes)
+        L = lib()
+        with torch.cuda.device(dev):
+            rowptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
+            col = torch.empty(max(2 * E, 1), dtype=torch.int32, device=dev)
+            meta = torch.zeros(2, dtype=torch.int64, device=dev)  # [nnz, status(int32 in low word)]
+            ws_bytes = L.dl_csr_build_workspace_bytes(E, N)
+            ws = _ws(ws_bytes, dev)
+            check(L.dl_csr_build(ptr(src), ptr(dst), E, N, ptr(rowptr), ptr(col), ptr(meta),
+                                 meta[1:].data_ptr(), ptr(ws), ws_bytes, stream_of(dev)),
+                  "dl_csr_build")
+            nnz, status = (int(x) for x in meta.cpu())
+            status = ctypes.c_int32(status & 0xFFFFFFFF).value
+            if status != 0:
+                raise _lib.DlError(status, "dl_csr_build")
+            del ws
+            col = col[:nnz].clone() if nnz < col.numel() else col
+        return cls(rowptr, col, N)
+
+    @classmethod
+    def from_edge_index(cls, edge_index: torch.Tensor, n_nodes: int) -> "Graph":
+        return cls.from_edges(edge_index[0], edge_index[1], n_nodes)
+
+    @classmethod
+    def from_dense(cls, adj: torch.Tensor) -> "Graph":
+        """From the dense adjacency the reference passes to ``Disentangle.forward`` (used as is,
+        any non-zero entry is an edge).  [ref: model.py:62]"""
+        require_cuda(adj, "adj")
+        if adj.dim() != 2 or adj.shape[0] != adj.shape[1]:
+            raise ValueError("adj must be a square [N,N] matrix")
+        dev = adj.device
+        a = adj.to(torch.float32).contiguous()
+        N = int(a.shape[0])
+        L = lib()
+        with torch.cuda.device(dev):
+            rowptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
+            ws = _ws((N + 1) * 8 + (1 << 20), dev)
+            check(L.dl_csr_from_dense(ptr(a), N, ptr(rowptr), None, ptr(ws), ws.numel(),
+                                      stream_of(dev)), "dl_csr_from_dense(count)")
+            nnz = int(rowptr[-1].item())
+            col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+            check(L.dl_csr_from_dense(ptr(a), N, ptr(rowptr), ptr(col), None, 0, stream_of(dev)),
+                  "dl_csr_from_dense(fill)")
+        return cls(rowptr, col[:nnz], N)
+
+    @classmethod
+    def from_csr(cls, rowptr: torch.Tensor, col: torch.Tensor) -> "Graph":
+        return cls(rowptr.to(torch.int64), col.to(torch.int32), int(rowptr.numel()) - 1)
+
+    # ------------------------------------------------------------------ integer kernels
+    def _build_items(self) -> None:
+        L = lib()
+        dev, N = self.device, self.N
+        with torch.cuda.device(dev):
+            self.perm = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+            self.bucket_off = torch.zeros(_lib.DL_N_BUCKETS + 1, dtype=torch.int64, device=dev)
+            ws_bytes = L.dl_degree_buckets_workspace_bytes(N)
+            ws = _ws(ws_bytes, dev)
+            check(L.dl_degree_buckets(ptr(self.rowptr), N, ptr(self.perm), ptr(self.bucket_off),
+                                      ptr(ws), ws_bytes, stream_of(dev)), "dl_degree_buckets")
+            self.bucket_off_host = self.bucket_off.cpu()
+            self.n_hub = int(self.bucket_off_host[_lib.DL_HUB_BUCKET_END])
+            self.hub_seg_ptr = torch.zeros(self.n_hub + 1, dtype=torch.int64, device=dev)
+            self.n_hub_items = 0
+            self.item_hub = torch.empty(1, dtype=torch.int32, device=dev)
+            if self.n_hub > 0:
+                check(L.dl_hub_items(ptr(self.rowptr), ptr(self.perm), self.n_hub,
+                                     ptr(self.hub_seg_ptr), None, 0, stream_of(dev)),
+                      "dl_hub_items(scan)")
+                self.n_hub_items = int(self.hub_seg_ptr[-1].item())
+                self.item_hub = torch.empty(max(self.n_hub_items, 1), dtype=torch.int32, device=dev)
+                check(L.dl_hub_items(ptr(self.rowptr), ptr(self.perm), self.n_hub,
+                                     ptr(self.hub_seg_ptr), ptr(self.item_hub), self.n_hub_items,
+                                     stream_of(dev)), "dl_hub_items(fill)")
+        self.struct = DlGraph(self.N, self.nnz, ptr(self.rowptr), ptr(self.col), ptr(self.perm),
+                              self.n_hub, self.n_hub_items, ptr(self.hub_seg_ptr),
+                              ptr(self.item_hub))
+        self._hub_ws = None
+
+    @property
+    def ref(self):
+        return ctypes.byref(self.struct)
+
+    def hub_scratch(self, width: int):
+        """fp32 scratch for hub-row partials of `width` floats per segment (None if no hubs)."""
+        need = self.n_hub_items * int(width)
+        if need == 0:
+            return None
+        if self._hub_ws is None or self._hub_ws.numel() < need:
+            self._hub_ws = torch.empty(need, dtype=torch.float32, device=self.device)
+        return self._hub_ws
+
+    def rev_index(self) -> torch.Tensor:
+        """rev[e] = position of the mirrored entry; raises if the pattern is not symmetric."""
+        if self._rev is None:
+            dev = self.device
+            with torch.cuda.device(dev):
+                rev = torch.empty(max(self.nnz, 1), dtype=torch.int64, device=dev)
+                status = torch.zeros(1, dtype=torch.int32, device=dev)
+                check(lib().dl_rev_index(ptr(self.rowptr), ptr(self.col), self.N, self.nnz, ptr(rev),
+                                         ptr(status), stream_of(dev)), "dl_rev_index")
+                code = int(status.item())
+            if code != 0:
+                raise _lib.DlError(code, "dl_rev_index")
+            self._rev = rev[:self.nnz]
+        return self._rev
+
+    def assert_symmetric(self) -> None:
+        self.rev_index()
+
+    def rows(self) -> torch.Tensor:
+        """Row id of every entry (torch op; for tests and dense views)."""
+        deg = self.rowptr[1:] - self.rowptr[:-1]
+        return torch.repeat_interleave(torch.arange(self.N, device=self.device), deg)
+
+    def degrees(self) -> torch.Tensor:
+        return self.rowptr[1:] - self.rowptr[:-1]

@@ -1,0 +1,273 @@
+"""torch.autograd bindings of the hot-path kernels (C ABI in include/disenlink_b200.h).
+
+    factor_aggregate(Z, graph, beta, T)  -> H            model.py:56-75   (attention + aggregation)
+    PairBatch(u, v, N) / pair_score(Z, H, batch, T)      model.py:109-113 on explicit pairs
+    allpairs_score(Z, H, T)              -> [N,N]        model.py:109-113 dense (small-N drop-in)
+
+Everything runs on the tensors' CUDA device through libdisenlink_b200.so; nothing here has a CPU
+implementation.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, require_cuda, stream_of
+from .graph import Graph
+
+
+def one_minus(beta: float) -> float:
+    """(1 - beta) evaluated in double like Python does at model.py:75, rounded to fp32 by ctypes."""
+    return 1.0 - float(beta)
+
+
+def _check_Z(Z: torch.Tensor, n_nodes: int):
+    require_cuda(Z, "Z")
+    if Z.dim() != 3 or Z.shape[0] != n_nodes:
+        raise ValueError(f"Z must be [N={n_nodes}, K, d], got {tuple(Z.shape)}")
+    if Z.dtype != torch.float32:
+        raise TypeError("Z must be float32 (parity target is the reference's fp32 path)")
+    K, d = int(Z.shape[1]), int(Z.shape[2])
+    if not (1 <= K <= _lib.DL_MAX_K and 1 <= d <= _lib.DL_MAX_D):
+        raise ValueError(f"unsupported factor shape K={K}, d={d} (K <= {_lib.DL_MAX_K}, d <= {_lib.DL_MAX_D})")
+    return K, d
+
+
+# --------------------------------------------------------------------------------------------
+# raw kernel wrappers (no autograd)
+# --------------------------------------------------------------------------------------------
+def edge_attn_fwd(graph: Graph, Z: torch.Tensor, T: float = 1.0):
+    """-> (kstar u8 [nnz], w f32 [nnz], s f32 [N,K]).  [ref: model.py:56-73]"""
+    K, d = _check_Z(Z, graph.N)
+    Z = Z.contiguous()
+    dev = Z.device
+    with torch.cuda.device(dev):
+        kstar = torch.empty(max(graph.nnz, 1), dtype=torch.uint8, device=dev)
+        w = torch.empty(max(graph.nnz, 1), dtype=torch.float32, device=dev)
+        s = torch.empty(graph.N, K, dtype=torch.float32, device=dev)
+        check(lib().dl_edge_attn_fwd(graph.ref, ptr(Z), K, d, float(T), ptr(kstar), ptr(w), ptr(s),
+                                     ptr(graph.hub_scratch(K)), stream_of(dev)), "dl_edge_attn_fwd")
+    return kstar[:graph.nnz], w[:graph.nnz], s
+
+
+def factor_spmm_fwd(graph: Graph, Z, kstar, w, s, beta: float):
+    """-> H [N,K,d].  [ref: model.py:75]"""
+    K, d = _check_Z(Z, graph.N)
+    Z = Z.contiguous()
+    dev = Z.device
+    with torch.cuda.device(dev):
+        H = torch.empty_like(Z)
+        check(lib().dl_factor_spmm_fwd(graph.ref, ptr(Z), ptr(kstar), ptr(w), ptr(s), K, d,
+                                       float(beta), one_minus(beta), ptr(H),
+                                       ptr(graph.hub_scratch(K * d)), stream_of(dev)),
+              "dl_factor_spmm_fwd")
+    return H
+
+
+def factor_bwd(graph: Graph, Z, G, kstar, w, s, beta: float, T: float = 1.0, dZ=None):
+    """dL/dZ through attention + aggregation given G = dL/dH; accumulated into dZ if given.
+    -> (dZ, r).  [ref: autograd of model.py:56-75]"""
+    K, d = _check_Z(Z, graph.N)
+    Z = Z.contiguous()
+    G = G.contiguous()
+    dev = Z.device
+    with torch.cuda.device(dev):
+        if dZ is None:
+            dZ = torch.zeros_like(Z)
+        r = torch.empty(graph.N, K, dtype=torch.float32, device=dev)
+        check(lib().dl_factor_bwd(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d,
+                                  float(beta), one_minus(beta), float(T), ptr(dZ), ptr(r),
+                                  ptr(graph.hub_scratch(K * d)), stream_of(dev)), "dl_factor_bwd")
+    return dZ, r
+
+
+class PairBatch:
+    """A batch of (u,v) node pairs resident on the GPU (int32 ids), plus -- built lazily, once --
+    the node-major incidence lists the atomic-free backward walks.
+
+    The training script's pair sets are fixed per run (main_disentangled.py:154-166), so one
+    PairBatch per split is built up front and reused every epoch."""
+
+    def __init__(self, u: torch.Tensor, v: torch.Tensor, n_nodes: int):
+        require_cuda(u, "u")
+        if u.shape != v.shape or u.dim() != 1:
+            raise ValueError("u and v must be 1-D tensors of equal length")
+        self.N = int(n_nodes)
+        self.P = int(u.numel())
+        if self.P:
+            lo = int(torch.minimum(u.min(), v.min()).item())
+            hi = int(torch.maximum(u.max(), v.max()).item())
+            if lo < 0 or hi >= self.N:
+                raise _lib.DlError(-3, "PairBatch")
+        self.u = u.to(torch.int32).contiguous()
+        self.v = v.to(torch.int32).contiguous()
+        self.device = u.device
+        self._inc = None
+
+    @classmethod
+    def from_pairs(cls, pairs: torch.Tensor, n_nodes: int) -> "PairBatch":
+        return cls(pairs[0], pairs[1], n_nodes)
+
+    def incidence(self):
+        """-> (Graph over incidence lists, inc_pair int32 [2P])."""
+        if self._inc is None:
+            dev, P, N = self.device, self.P, self.N
+            L = lib()
+            with torch.cuda.device(dev):
+                inc_ptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
+                inc_other = torch.empty(max(2 * P, 1), dtype=torch.int32, device=dev)
+                inc_pair = torch.empty(max(2 * P, 1), dtype=torch.int32, device=dev)
+                ws_bytes = L.dl_pair_incidence_workspace_bytes(P, N)
+                ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+                check(L.dl_pair_incidence(ptr(self.u), ptr(self.v), P, N, ptr(inc_ptr), ptr(inc_other),
+                                          ptr(inc_pair), ptr(ws), ws_bytes, stream_of(dev)),
+                      "dl_pair_incidence")
+                g = Graph(inc_ptr, inc_other[:2 * P], N)
+            self._inc = (g, inc_pair[:2 * P])
+        return self._inc
+
+
+def pair_score_fwd(Z, H, batch: PairBatch, T: float = 1.0, want_logit=True, want_prob=True):
+    K, d = _check_Z(Z, batch.N)
+    Z = Z.contiguous()
+    H = H.contiguous()
+    dev = Z.device
+    with torch.cuda.device(dev):
+        logit = torch.empty(max(batch.P, 1), dtype=torch.float32, device=dev) if want_logit else None
+        prob = torch.empty(max(batch.P, 1), dtype=torch.float32, device=dev) if want_prob else None
+        check(lib().dl_pair_score_fwd(ptr(batch.u), ptr(batch.v), batch.P, ptr(Z), ptr(H), batch.N,
+                                      K, d, float(T), ptr(logit), ptr(prob), stream_of(dev)),
+              "dl_pair_score_fwd")
+    return (logit[:batch.P] if want_logit else None), (prob[:batch.P] if want_prob else None)
+
+
+def pair_score_bwd(Z, H, batch: PairBatch, dS, T: float = 1.0):
+    """-> (dZ, dH) of the decoder given dS = dL/dlogit."""
+    K, d = _check_Z(Z, batch.N)
+    Z = Z.contiguous()
+    H = H.contiguous()
+    dS = dS.contiguous().to(torch.float32)
+    dev = Z.device
+    g, inc_pair = batch.incidence()
+    with torch.cuda.device(dev):
+        dZ = torch.empty_like(Z)
+        dH = torch.empty_like(Z)
+        check(lib().dl_pair_score_bwd(g.ref, ptr(inc_pair), ptr(Z), ptr(H), ptr(dS), K, d, float(T),
+                                      ptr(dZ), ptr(dH), ptr(g.hub_scratch(2 * K * d)),
+                                      stream_of(dev)), "dl_pair_score_bwd")
+    return dZ, dH
+
+
+# --------------------------------------------------------------------------------------------
+# autograd Functions
+# --------------------------------------------------------------------------------------------
+class _FactorAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Z, graph, beta, T):
+        Zc = Z.contiguous()
+        kstar, w, s = edge_attn_fwd(graph, Zc, T)
+        H = factor_spmm_fwd(graph, Zc, kstar, w, s, beta)
+        ctx.graph, ctx.beta, ctx.T = graph, float(beta), float(T)
+        ctx.save_for_backward(Zc, kstar, w, s)
+        ctx.mark_non_differentiable(kstar, w, s)
+        return H, kstar, w, s
+
+    @staticmethod
+    def backward(ctx, G, _gk, _gw, _gs):
+        Z, kstar, w, s = ctx.saved_tensors
+        dZ, _ = factor_bwd(ctx.graph, Z, G.contiguous(), kstar, w, s, ctx.beta, ctx.T)
+        return dZ, None, None, None
+
+
+def factor_aggregate(Z, graph: Graph, beta: float, T: float = 1.0, return_attention=False):
+    """H[i,k] = beta Z[i,k] + (1-beta) sum_j att_k[i,j] Z[j,k] with the reference's hard-routed,
+    source-normalised attention.  Differentiable w.r.t. Z.  [ref: model.py:55-77]"""
+    H, kstar, w, s = _FactorAggregate.apply(Z, graph, beta, T)
+    return (H, kstar, w, s) if return_attention else H
+
+
+class _PairScore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Z, H, batch, T, as_prob):
+        Zc, Hc = Z.contiguous(), H.contiguous()
+        logit, prob = pair_score_fwd(Zc, Hc, batch, T, want_logit=not as_prob, want_prob=as_prob)
+        out = prob if as_prob else logit
+        ctx.batch, ctx.T, ctx.as_prob = batch, float(T), bool(as_prob)
+        ctx.save_for_backward(Zc, Hc, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        Z, H, out = ctx.saved_tensors
+        if ctx.as_prob:
+            dS = gout * (1.0 - out) * out   # torch's sigmoid backward: grad * (1 - y) * y
+        else:
+            dS = gout
+        dZ, dH = pair_score_bwd(Z, H, ctx.batch, dS, ctx.T)
+        return dZ, dH, None, None, None
+
+
+def pair_score(Z, H, batch: PairBatch, T: float = 1.0, as_prob: bool = True):
+    """sigmoid(sum_k exp(z_u^k.z_v^k/T) (h_u^k.h_v^k)) (or the logit) for every pair of the batch.
+    Differentiable w.r.t. Z and H.  [ref: model.py:109-113]"""
+    return _PairScore.apply(Z, H, batch, T, as_prob)
+
+
+class _AllPairsScore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Z, H, T):
+        K, d = _check_Z(Z, Z.shape[0])
+        Zc, Hc = Z.contiguous(), H.contiguous()
+        N = int(Z.shape[0])
+        dev = Z.device
+        with torch.cuda.device(dev):
+            prob = torch.empty(N, N, dtype=torch.float32, device=dev)
+            check(lib().dl_allpairs_score_fwd(ptr(Zc), ptr(Hc), N, K, d, float(T), ptr(prob),
+                                              stream_of(dev)), "dl_allpairs_score_fwd")
+        ctx.T = float(T)
+        ctx.save_for_backward(Zc, Hc, prob)
+        return prob
+
+    @staticmethod
+    def backward(ctx, gP):
+        Z, H, prob = ctx.saved_tensors
+        N, K, d = (int(x) for x in Z.shape)
+        dev = Z.device
+        dS = gP * (1.0 - prob) * prob
+        dSsym = (dS + dS.t()).contiguous()
+        with torch.cuda.device(dev):
+            dZ = torch.empty_like(Z)
+            dH = torch.empty_like(Z)
+            check(lib().dl_allpairs_score_bwd(ptr(Z), ptr(H), ptr(dSsym), N, K, d, ctx.T, ptr(dZ),
+                                              ptr(dH), stream_of(dev)), "dl_allpairs_score_bwd")
+        return dZ, dH, None
+
+
+def allpairs_score(Z, H, T: float = 1.0):
+    """Dense [N,N] link_pred of model.py:109-113 (small N: the unmodified script's contract)."""
+    return _AllPairsScore.apply(Z, H, T)
+
+
+def dense_alpha0(Z, T: float = 1.0):
+    """alpha0 [K,N,N] = exp(Z_k Z_k^T / T), second return of Disentangle_layer (model.py:57,77)."""
+    K, d = _check_Z(Z, Z.shape[0])
+    Zc = Z.detach().contiguous()
+    N = int(Z.shape[0])
+    dev = Z.device
+    with torch.cuda.device(dev):
+        out = torch.empty(K, N, N, dtype=torch.float32, device=dev)
+        check(lib().dl_dense_alpha0(ptr(Zc), N, K, d, float(T), ptr(out), stream_of(dev)),
+              "dl_dense_alpha0")
+    return out
+
+
+def dense_att(graph: Graph, kstar, w, s, K: int):
+    """att list of Disentangle_layer as one [K,N,N] tensor (model.py:70-74,77)."""
+    dev = graph.device
+    with torch.cuda.device(dev):
+        out = torch.zeros(K, graph.N, graph.N, dtype=torch.float32, device=dev)
+        check(lib().dl_dense_att(graph.ref, ptr(kstar), ptr(w), ptr(s), K, ptr(out), stream_of(dev)),
+              "dl_dense_att")
+    return out

@@ -1,0 +1,174 @@
+/*
+ * disenlink_b200.h -- C ABI of libdisenlink_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * The reference (sjz5202/DisenLink) has no FFI: its hot path is the Python nn.Module API of
+ * model.py called by main_disentangled.py.  This ABI is what a binding for that path calls; the
+ * Python side (disenlink_b200/model.py, a drop-in for the reference's model.py) reaches it through
+ * ctypes.  For every entry point the reference lines it replaces are cited as
+ * [ref: file:line] with paths relative to the reference repository root.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only
+ *     enqueue work; they never synchronise unless stated.
+ *   - every function returns 0 on success, a negative DL_E* code for argument errors, or a
+ *     positive cudaError_t value when the CUDA runtime reported one.  Nothing throws.
+ *   - re-entrant, no global state; outputs are caller-allocated; nothing is freed across the ABI.
+ *   - layouts: Z, H, G, dZ, dH are [N, K, d] fp32 row-major (identical in memory to
+ *     torch.cat(h_list, dim=1) of model.py:114); rowptr int64 [N+1]; col int32 [nnz] ascending
+ *     inside a row; kstar uint8 [nnz]; w fp32 [nnz]; s, r fp32 [N, K].
+ */
+#ifndef DISENLINK_B200_H
+#define DISENLINK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DL_OK 0
+#define DL_EINVAL (-1)      /* bad argument (null pointer, negative size, K or d out of range) */
+#define DL_EWORKSPACE (-2)  /* workspace too small */
+#define DL_ERANGE (-3)      /* an edge endpoint / pair id is outside [0, N) */
+#define DL_EASYM (-4)       /* adjacency pattern is not symmetric */
+#define DL_EUNSUPPORTED (-5)
+
+#define DL_MAX_K 32         /* kstar is stored in 5 bits of a byte; K-factor count limit */
+#define DL_MAX_D 256        /* per-factor width limit */
+#define DL_SEG 512          /* edges per work item; rows with more edges are split (hub rows) */
+#define DL_N_BUCKETS 33     /* degree classes: bucket b holds rows whose degree has bit length 32-b */
+#define DL_HUB_BUCKET_END 23 /* buckets [0,23) hold degree classes 32..10, i.e. degree >= 512 */
+
+typedef void* dl_stream_t;
+
+int dl_abi_version(void);
+const char* dl_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) adjacency -> CSR, reverse-edge index, degree buckets and work items.  Integer work.
+ * [ref: main_disentangled.py:137-142]  adj = to_dense(train edges); adj[adj!=0]=1;
+ *       adj_sym = adj + adj.t(); adj_sym[adj_sym!=0]=1   (duplicates collapse, diagonal kept)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Bytes of scratch dl_csr_build needs for E directed input edges. */
+size_t dl_csr_build_workspace_bytes(int64_t E, int64_t N);
+
+/* src,dst int64 [E] -> rowptr [N+1], col [capacity >= 2E], *nnz_out (device int64).
+ * status_out (device int32): 0, or DL_ERANGE if an endpoint is outside [0,N) (outputs undefined). */
+int dl_csr_build(const int64_t* src, const int64_t* dst, int64_t E, int64_t N, int64_t* rowptr,
+                 int32_t* col, int64_t* nnz_out, int32_t* status_out, void* ws, size_t ws_bytes,
+                 dl_stream_t stream);
+
+/* Same, from an already dense 0/1 (any non-zero counts) [N,N] fp32 adjacency that is used as is
+ * (no symmetrisation): the drop-in path of Disentangle.forward(x, adj).  [ref: model.py:62]
+ * Two calls: count (col == NULL) fills rowptr; fill (col != NULL) writes the columns. */
+int dl_csr_from_dense(const float* adj, int64_t N, int64_t* rowptr, int32_t* col, void* ws,
+                      size_t ws_bytes, dl_stream_t stream);
+
+/* rev[e] = index of entry (j,i) for entry e=(i,j).  status_out = DL_EASYM if some entry has no
+ * mirror.  The backward kernels rely on a symmetric pattern (always true for adj_sym). */
+int dl_rev_index(const int64_t* rowptr, const int32_t* col, int64_t N, int64_t nnz, int64_t* rev,
+                 int32_t* status_out, dl_stream_t stream);
+
+/* Degree-sorted row bucketing: perm [N] = row ids ordered by degree class descending (stable),
+ * bucket_off [DL_N_BUCKETS+1] (device int64) = start of each class in perm. */
+size_t dl_degree_buckets_workspace_bytes(int64_t N);
+int dl_degree_buckets(const int64_t* rowptr, int64_t N, int32_t* perm, int64_t* bucket_off,
+                      void* ws, size_t ws_bytes, dl_stream_t stream);
+
+/* Work items for hub rows (degree >= DL_SEG, i.e. degree class >= 10), which are the first
+ * n_hub = bucket_off[DL_HUB_BUCKET_END] rows of perm.
+ * hub_seg_ptr [n_hub+1] (device int64) = running count of DL_SEG-edge segments;
+ * item_hub [n_items] = hub index of every segment.  Call once with item_hub == NULL to fill
+ * hub_seg_ptr (the caller reads hub_seg_ptr[n_hub] to size item_hub), then again to fill it. */
+int dl_hub_items(const int64_t* rowptr, const int32_t* perm, int64_t n_hub, int64_t* hub_seg_ptr,
+                 int32_t* item_hub, int64_t n_items, dl_stream_t stream);
+
+/* Everything a kernel needs to walk the graph.  Plain-old-data, passed by pointer (host memory). */
+typedef struct dl_graph {
+  int64_t N;
+  int64_t nnz;
+  const int64_t* rowptr;       /* [N+1] */
+  const int32_t* col;          /* [nnz] */
+  const int32_t* perm;         /* [N] degree-class order, hub rows first */
+  int64_t n_hub;               /* rows with degree >= DL_SEG */
+  int64_t n_hub_items;         /* total segments of hub rows */
+  const int64_t* hub_seg_ptr;  /* [n_hub+1] */
+  const int32_t* item_hub;     /* [n_hub_items] */
+} dl_graph;
+
+/* ------------------------------------------------------------------------------------------
+ * (2) per-edge K-factor attention with hard routing.
+ * [ref: model.py:56-73]  q_k = z_i^k . z_j^k / T; a = softmax_k(q); kstar = argmax_k a (first
+ *       max); w = a[kstar]; s[r,k] = sum of w over row r's entries routed to k, 0 -> 1.
+ * hub_ws: fp32 scratch of dl_hub_scratch_floats(g, K) floats (may be NULL when n_hub == 0).
+ * ------------------------------------------------------------------------------------------ */
+size_t dl_hub_scratch_floats(const dl_graph* g_host, int64_t width);
+
+int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float T,
+                     uint8_t* kstar, float* w, float* s, float* hub_ws, dl_stream_t stream);
+
+/* (3) per-factor gather / segment-sum aggregation with the beta residual.
+ * [ref: model.py:75]  H[i,k] = beta Z[i,k] + (1-beta) sum_{j: kstar(i,j)=k} w_ij / s[j,k] Z[j,k]
+ * one_minus_beta is passed separately because Python evaluates (1 - beta) in double.
+ * hub_ws: dl_hub_scratch_floats(g, K*d) floats. */
+int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
+                       const float* w, const float* s, int K, int d, float beta,
+                       float one_minus_beta, float* H, float* hub_ws, dl_stream_t stream);
+
+/* (4) backward of (2)+(3) w.r.t. Z given G = dL/dH.  dZ is ACCUMULATED into (it may already
+ * hold the decoder's direct gradient); r [N,K] is scratch/output.  Closed form in DESIGN.md.
+ * [ref: autograd of model.py:56-75].  hub_ws: dl_hub_scratch_floats(g, K*d) floats. */
+int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const uint8_t* kstar,
+                  const float* w, const float* s, int K, int d, float beta, float one_minus_beta,
+                  float T, float* dZ, float* r, float* hub_ws, dl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (5) factor-weighted link-pair scoring over explicit (u,v) batches.
+ * [ref: model.py:109-113]  logit = sum_k exp(z_u^k.z_v^k/T) (h_u^k.h_v^k); prob = sigmoid(logit)
+ * logit / prob may each be NULL (not both).  Ids must lie in [0,N); the caller validates them once
+ * per batch (dl_pair_incidence reports DL_ERANGE-free lists only for valid ids).
+ * ------------------------------------------------------------------------------------------ */
+int dl_pair_score_fwd(const int32_t* u, const int32_t* v, int64_t P, const float* Z,
+                      const float* H, int64_t N, int K, int d, float T, float* logit, float* prob,
+                      dl_stream_t stream);
+
+/* Node-major incidence lists of a pair batch (built once per batch, integer work):
+ * inc_ptr [N+1] int64, inc_other [2P] int32 (the other endpoint), inc_pair [2P] int32 (pair id),
+ * in pair order inside a node.  Needed by the atomic-free backward. */
+size_t dl_pair_incidence_workspace_bytes(int64_t P, int64_t N);
+int dl_pair_incidence(const int32_t* u, const int32_t* v, int64_t P, int64_t N, int64_t* inc_ptr,
+                      int32_t* inc_other, int32_t* inc_pair, void* ws, size_t ws_bytes,
+                      dl_stream_t stream);
+
+/* Backward of the decoder given dS = dL/dlogit [P].  `inc_host` is the incidence structure seen
+ * as a graph (rowptr = inc_ptr, col = inc_other, plus perm / hub items from dl_degree_buckets and
+ * dl_hub_items, so nodes that take part in many pairs are split like hub rows).  dZ, dH [N,K,d]
+ * are OVERWRITTEN (every node's row is written exactly once; no atomics).
+ * hub_ws: dl_hub_scratch_floats(inc, 2*K*d) floats.  [ref: autograd of model.py:109-113] */
+int dl_pair_score_bwd(const dl_graph* inc_host, const int32_t* inc_pair, const float* Z,
+                      const float* H, const float* dS, int K, int d, float T, float* dZ, float* dH,
+                      float* hub_ws, dl_stream_t stream);
+
+/* Dense all-pairs decoder for the small-N drop-in contract: out [N,N] = sigmoid(logit(u,v)).
+ * [ref: model.py:109-113, consumed by main_disentangled.py:195,202,217 via boolean masks] */
+int dl_allpairs_score_fwd(const float* Z, const float* H, int64_t N, int K, int d, float T,
+                          float* prob, dl_stream_t stream);
+/* dSsym [N,N] = dS + dS^T with dS = dL/dlogit (dense; zeros are skipped) -> dZ, dH overwritten. */
+int dl_allpairs_score_bwd(const float* Z, const float* H, const float* dSsym, int64_t N, int K,
+                          int d, float T, float* dZ, float* dH, dl_stream_t stream);
+
+/* Dense [K,N,N] views of the layer's internals for API parity with Disentangle_layer.forward's
+ * second and third returns (alpha0 = exp(zz^T/T); att).  Small N only.  [ref: model.py:57,74,77] */
+int dl_dense_alpha0(const float* Z, int64_t N, int K, int d, float T, float* alpha0,
+                    dl_stream_t stream);
+int dl_dense_att(const dl_graph* g_host, const uint8_t* kstar, const float* w, const float* s,
+                 int K, float* att, dl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISENLINK_B200_H */
