@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""bench.py -- factor-aggregation edges/s (fwd+bwd) and link-pair scores/s on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|mid|tiny] [--impl reference]
+
+One "step" = one pass of the hot path over the whole graph and pair batch:
+    attention -> aggregation -> pair scoring -> BCE gradient -> decoder backward -> factor backward
+`value` = nnz / (t_attention + t_aggregation + t_factor_backward)  [edges/s, BASELINE.json metric],
+with inputs resident in HBM; per-kernel CUDA-event times and the HBM roofline of the dominant
+kernel are reported next to it.  `e2e` runs the same pass through the public autograd API
+(`ops.link_bce_loss` + backward) with Z copied from pinned host memory and the loss / scores read
+back every step.  `cpu_baseline` times the CPU oracle (a port of the reference's math, the dense
+reference itself cannot run at these sizes) on a bounded sample on the box's host cores.
+N > 1 (torchrun): the same graph is node-partitioned across the ranks (strong scaling) with NCCL
+all-gathers between the kernels (disenlink_b200/partition.py).
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[4]: synthetic power-law graph 50M nodes / 500M edges, K=8, D=128, 100M pairs
+    "c5": dict(N=50_000_000, E=500_000_000, K=8, d=16, P=100_000_000, beta=0.5, T=1.0,
+               name="synthetic power-law 50M nodes / 500M directed edges, K=8, d=16 (D=128), 100M link pairs"),
+    # BASELINE.json configs[3] scale: snap-patents-sized synthetic
+    "c4": dict(N=2_923_922, E=13_975_788, K=8, d=16, P=16_000_000, beta=0.5, T=1.0,
+               name="snap-patents-scale synthetic 2.92M nodes / 13.98M directed edges, K=8, d=16"),
+    "mid": dict(N=5_000_000, E=50_000_000, K=8, d=16, P=10_000_000, beta=0.5, T=1.0,
+                name="synthetic power-law 5M nodes / 50M directed edges, K=8, d=16 (1/10 of c5)"),
+    "tiny": dict(N=200_000, E=2_000_000, K=8, d=16, P=400_000, beta=0.5, T=1.0,
+                 name="synthetic power-law 200k nodes / 2M directed edges (smoke)"),
+}
+CPU_SAMPLE = dict(N=500_000, E=5_000_000, P=1_000_000)   # 1/100 of c5, same generator
+M_NEG = 5
+POWER = 3.0   # endpoint rank ~ N * U^3  ->  degree(rank) ~ rank^(-2/3), degree exponent alpha = 2.5
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs (torch ops; same code on cpu and cuda)
+# ------------------------------------------------------------------------------------------------
+def gen_edges(N, E, seed, device):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    src = torch.empty(E, dtype=torch.int64, device=device)
+    dst = torch.empty(E, dtype=torch.int64, device=device)
+    A, B = 7919, 104729   # affine node-id shuffle (A coprime to N) so hubs are spread over the id range
+    while math.gcd(A, N) != 1:
+        A += 2
+    chunk = 1 << 26
+    for out in (src, dst):
+        for a in range(0, E, chunk):
+            b = min(E, a + chunk)
+            u = torch.rand(b - a, generator=g, device=device, dtype=torch.float64)
+            ids = (u.pow_(POWER) * N).to(torch.int64).clamp_(max=N - 1)
+            out[a:b] = (ids * A + B) % N
+    return src, dst
+
+
+def gen_pairs(rowptr, col, N, P, seed, device):
+    """P = P_pos * (1 + M_NEG): positives drawn from CSR entries, M_NEG uniform negatives sharing u
+    with each positive (main_disentangled.py:159-163), sorted by u."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed + 1)
+    nnz = int(col.numel())
+    P_pos = max(P // (1 + M_NEG), 1)
+    e = torch.randint(0, max(nnz, 1), (P_pos,), generator=g, device=device)
+    pu = torch.searchsorted(rowptr, e, right=True) - 1
+    pv = col[e].to(torch.int64)
+    nu = pu.repeat(M_NEG)
+    nv = torch.randint(0, N, (P_pos * M_NEG,), generator=g, device=device)
+    u = torch.cat([pu, nu])
+    v = torch.cat([pv, nv])
+    lab = torch.cat([torch.ones(P_pos, device=device), torch.zeros(P_pos * M_NEG, device=device)])
+    wts = torch.cat([torch.full((P_pos,), 1.0 / P_pos, device=device),
+                     torch.full((P_pos * M_NEG,), 1.0 / (M_NEG * P_pos * M_NEG), device=device)])
+    order = torch.sort(u, stable=True).indices
+    return u[order], v[order], lab[order], wts[order]
+
+
+def gen_Z(n_rows, K, d, seed, device):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed + 2)
+    Z = torch.empty(n_rows, K, d, dtype=torch.float32, device=device)
+    chunk = 1 << 22
+    for a in range(0, n_rows, chunk):
+        b = min(n_rows, a + chunk)
+        Z[a:b] = torch.randn(b - a, K, d, generator=g, device=device) * (d ** -0.25)  # q = O(1)
+    return Z
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes
+# ------------------------------------------------------------------------------------------------
+def alg_bytes(nnz, N, K, d, P):
+    D = K * d
+    return {
+        "attn_fwd": nnz * (4 + 4 * D + 5) + N * (4 * D + 4 * K) + 8 * (N + 1),
+        "spmm_fwd": nnz * (4 + 5 + 4 + 4 * d) + N * (8 * D + 4 * K) + 8 * (N + 1),
+        "bwd_gather": nnz * (9 + 4 * d) + N * (12 * D + 8 * K) + 8 * (N + 1),
+        "bwd_edges": nnz * (17 + 4 * D + 4 * d) + N * (12 * D + 8 * K) + 8 * (N + 1),
+        "pair_fwd": P * (16 * D + 12),
+        "pair_bwd": P * (32 * D + 16),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index=0):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on a bounded sample (all host threads)
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(K, d, beta, T, steps=2, warmup=1):
+    import numpy as np
+    import torch
+    from oracle import oracle
+    threads = os.cpu_count() or 1
+    oracle.set_num_threads(threads)
+    cs = CPU_SAMPLE
+    src, dst = gen_edges(cs["N"], cs["E"], 0, "cpu")
+    rowptr, col = oracle.csr_from_edges(src.numpy(), dst.numpy(), cs["N"])
+    u, v, lab, wts = gen_pairs(torch.from_numpy(rowptr), torch.from_numpy(col), cs["N"], cs["P"], 0, "cpu")
+    Z = gen_Z(cs["N"], K, d, 0, "cpu").numpy()
+    u, v, lab, wts = u.numpy(), v.numpy(), lab.numpy(), wts.numpy()
+    nnz = int(col.size)
+    t_factor, t_pair_fwd, t_all = [], [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        ks, w, s = oracle.edge_attn_fwd(rowptr, col, Z, T)
+        H = oracle.factor_spmm_fwd(rowptr, col, Z, ks, w, s, beta)
+        t1 = time.perf_counter()
+        _, prob = oracle.pair_score_fwd(u, v, Z, H, T)
+        t2 = time.perf_counter()
+        dS = ((prob - lab) * wts).astype(np.float32)
+        dZp, dH = oracle.pair_score_bwd(u, v, Z, H, dS, T)
+        t3 = time.perf_counter()
+        oracle.factor_bwd(rowptr, col, Z, dH, ks, w, s, beta, T, dZ_init=dZp)
+        t4 = time.perf_counter()
+        if it >= warmup:
+            t_factor.append((t1 - t0) + (t4 - t3))
+            t_pair_fwd.append(t2 - t1)
+            t_all.append(t4 - t0)
+    tf = sum(t_factor) / len(t_factor)
+    return {"value": nnz / tf, "unit": "edges/s", "cores": threads, "kind": "port",
+            "pair_scores_per_s": cs["P"] / (sum(t_pair_fwd) / len(t_pair_fwd)),
+            "ms_per_step": 1e3 * sum(t_all) / len(t_all),
+            "sample": f"same power-law generator at 1/100 scale: N={cs['N']}, E={cs['E']} directed edges "
+                      f"(nnz={nnz}), P={cs['P']} pairs, K={K}, d={d}; {steps} timed steps after {warmup} "
+                      f"warm-up; C oracle (oracle/disen_oracle.c, OpenMP, {threads} threads)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU math.  The dense model.py path needs
+    (9K+6) N^2 4 bytes (121 GB already at N = 19 717) and /root/reference does not exist on the GPU
+    box, so this arm times the oracle port of the same math, all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    cb = cpu_baseline(wl["K"], wl["d"], wl["beta"], wl["T"], steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": "factor-agg edges/s (fwd+bwd)", "value": cb["value"],
+            "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "K": wl["K"], "d": wl["d"]},
+            "pair_scores_per_s": cb["pair_scores_per_s"],
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "edges/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+PHASES = ["ag_Z", "attn_fwd", "ag_s", "spmm_fwd", "ag_H", "pair_fwd", "ag_prob", "loss", "pair_bwd",
+          "ag_dH", "bwd_gather", "ag_r", "bwd_edges"]
+KERNEL_PHASES = ["attn_fwd", "spmm_fwd", "pair_fwd", "pair_bwd", "bwd_gather", "bwd_edges"]
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from disenlink_b200 import _lib, ops
+    from disenlink_b200.partition import PartitionedLinkStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()  # fail loudly if the extension is missing
+
+    wl = dict(WORKLOADS[args.workload])
+    N, E, K, d, P, beta, T = (wl[k] for k in ("N", "E", "K", "d", "P", "beta", "T"))
+    D = K * d
+    # memory guard: ~4 [N,K,d] fp32 buffers + graph + pairs must fit (per rank the node arrays are full size)
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    need = int(4.4 * N * D * 4) + 2 * E * 10 // world + 56 * E // world + 16 * E + P * 50 + (4 << 30)
+    need = max(int(4.4 * N * D * 4) + 2 * E * 10 // world + P * 50, 16 * E + 56 * E // world) + (4 << 30)
+    if need > free_b:
+        raise SystemExit(f"workload {args.workload} needs ~{need / 2**30:.0f} GiB, {free_b / 2**30:.0f} GiB free")
+
+    t_setup = time.perf_counter()
+    src, dst = gen_edges(N, E, 0, dev)
+    from disenlink_b200.graph import Graph
+    # every rank draws the same pairs: positives are directed edge columns (each is an entry of
+    # adj_sym), M_NEG uniform negatives share u with their positive (main_disentangled.py:159-163);
+    # sorted by u so the (1 + M_NEG) pairs of one u are adjacent
+    gp = torch.Generator(device=dev).manual_seed(1)
+    P_pos = max(P // (1 + M_NEG), 1)
+    e = torch.randint(0, E, (P_pos,), generator=gp, device=dev)
+    pu, pv = src[e], dst[e]
+    nu = pu.repeat(M_NEG)
+    nv = torch.randint(0, N, (P_pos * M_NEG,), generator=gp, device=dev)
+    u, v = torch.cat([pu, nu]), torch.cat([pv, nv])
+    lab = torch.cat([torch.ones(P_pos, device=dev), torch.zeros(P_pos * M_NEG, device=dev)])
+    wts = torch.cat([torch.full((P_pos,), 1.0 / P_pos, device=dev),
+                     torch.full((P_pos * M_NEG,), 1.0 / (M_NEG * P_pos * M_NEG), device=dev)])
+    order = torch.sort(u, stable=True).indices
+    u, v, lab, wts = u[order], v[order], lab[order], wts[order]
+    del e, pu, pv, nu, nv, order
+    P = int(u.numel())
+
+    events = []
+
+    def mark(name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(dev))
+        events.append((name, ev))
+
+    step = PartitionedLinkStep(src, dst, N, u, v, lab, wts, K, d, beta, T, world=world, rank=rank,
+                               device=dev, mark=mark)
+    del src, dst
+    torch.cuda.empty_cache()
+    part = step.part
+    nnz_local = step.graph.nnz
+    nnz_global = nnz_local
+    if world > 1:
+        t = torch.tensor([nnz_local], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        nnz_global = int(t.item())
+    Z = gen_Z(part.n_pad, K, d, 0, dev)   # every rank generates the same full Z; only own rows are "its"
+    torch.cuda.synchronize(dev)
+    t_setup = time.perf_counter() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-timed loop ----
+    for _ in range(args.warmup):
+        step.run(Z)
+    barrier()
+    events.clear()
+    launches0 = _lib.launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev_a.record(torch.cuda.current_stream(dev))
+    for _ in range(args.steps):
+        step.run(Z)
+    ev_b.record(torch.cuda.current_stream(dev))
+    barrier()
+    clocks = sampler.stop()
+    abi_calls = _lib.launches - launches0
+    total_ms = ev_a.elapsed_time(ev_b)
+    # per-phase times from consecutive events
+    phase_ms = {p: 0.0 for p in PHASES}
+    for (n0, e0), (n1, e1) in zip(events[:-1], events[1:]):
+        if n1 != "begin":
+            phase_ms[n1] += e0.elapsed_time(e1)
+    phase_ms = {p: v / args.steps for p, v in phase_ms.items()}
+    loss_val = float(step.loss.item())
+    if world > 1:
+        tt = torch.tensor([total_ms] + [phase_ms[p] for p in PHASES], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt[0].item())
+        phase_ms = {p: float(x) for p, x in zip(PHASES, tt[1:].tolist())}
+    ms_per_step = total_ms / args.steps
+    t_factor = phase_ms["attn_fwd"] + phase_ms["spmm_fwd"] + phase_ms["bwd_gather"] + phase_ms["bwd_edges"]
+    t_comm_factor = phase_ms["ag_Z"] + phase_ms["ag_s"] + phase_ms["ag_H"] + phase_ms["ag_dH"] + phase_ms["ag_r"]
+    value = nnz_global / ((t_factor + t_comm_factor) * 1e-3)
+    pair_rate = P / ((phase_ms["pair_fwd"] + phase_ms["ag_prob"]) * 1e-3)
+
+    # ---- roofline of the dominant kernel (per-rank bytes / per-rank time) ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    ab = alg_bytes(nnz_local, part.n_local, K, d, 0)
+    ab["pair_fwd"] = (step.p_hi - step.p_lo) * (16 * D + 12)
+    # node-major decoder backward: per incidence the other endpoint's Z and H rows + 3 ids/floats,
+    # per node 2 rows in and 2 rows out (less than SURVEY's scatter-form P*(32D+16): see DESIGN.md)
+    ab["pair_bwd"] = int(step.inc.nnz) * (8 * D + 12) + part.n_local * 16 * D
+    launches_per_step = 6 + (4 if step.graph.n_hub > 0 else 0) + (1 if step.inc.n_hub > 0 else 0)
+    kernels = {}
+    for kname in KERNEL_PHASES:
+        ms = phase_ms[kname]
+        gbs = ab[kname] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        kernels[kname] = {"ms": round(ms, 4), "alg_bytes": int(ab[kname]), "GB/s": round(gbs, 1),
+                          "frac": round(gbs / peak, 4)}
+    dom = max(KERNEL_PHASES, key=lambda k: phase_ms[k])
+    fwd_bwd_bytes = ab["attn_fwd"] + ab["spmm_fwd"] + ab["bwd_gather"] + ab["bwd_edges"]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GB/s"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "factor_agg_fwd_bwd": {"alg_bytes": int(fwd_bwd_bytes),
+                                       "GB/s": round(fwd_bwd_bytes / (t_factor * 1e-3) / 1e9, 1),
+                                       "frac": round(fwd_bwd_bytes / (t_factor * 1e-3) / 1e9 / peak, 4)}}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(dom)
+        except Exception:
+            pass
+
+    # ---- end to end through the public autograd API, host buffers ----
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        del step
+        torch.cuda.empty_cache()
+        g_full = Graph.from_edges(*gen_edges(N, E, 0, dev), N)
+        batch = ops.PairBatch(u, v, N)
+        batch.incidence()
+        Z_host = torch.empty(N, K, d, dtype=torch.float32).pin_memory()
+        Z_host.copy_(Z[:N])
+        del Z
+        torch.cuda.empty_cache()
+        prob_host = torch.empty(P, dtype=torch.float32).pin_memory()
+        Zd = torch.empty(N, K, d, dtype=torch.float32, device=dev)
+
+        def e2e_step():
+            Zd.copy_(Z_host, non_blocking=True)
+            Zg = Zd.requires_grad_(True)
+            loss, prob, _ = ops.link_bce_loss(Zg, g_full, batch, lab, wts, beta, T)
+            loss.backward()
+            prob_host.copy_(prob, non_blocking=True)
+            val = loss.item()
+            Zg.grad = None
+            Zd.requires_grad_(False)
+            return val
+
+        for _ in range(max(args.warmup, 1)):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_loss = e2e_step()
+        torch.cuda.synchronize(dev)
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        e2e = {"value": g_full.nnz / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": round(e2e_ms, 3),
+               "h2d_bytes_per_step": int(N * D * 4), "d2h_bytes_per_step": int(P * 4 + 4),
+               "api": "ops.link_bce_loss(Z, graph, pairs, labels, weights).backward(); Z from pinned host "
+                      "memory, loss + P scores read back", "loss": e2e_loss}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cb = cpu_baseline(K, d, beta, T) if (world == 1 and not args.no_cpu) else None
+
+    line = {
+        "metric": "factor-agg edges/s (fwd+bwd)", "value": value, "unit": "edges/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": wl["name"], "N": N, "E_directed": E, "nnz": nnz_global, "K": K, "d": d, "P": P,
+                   "beta": beta, "T": T, "parallelism": "1 GPU" if world == 1 else f"node-partitioned x{world}, NCCL all-gather",
+                   "l2": f"inputs exceed L2: Z alone is {N * D * 4 / 2**30:.1f} GiB vs 126 MB L2 (no flush needed)",
+                   "value_definition": "nnz / (attention + aggregation + both backward passes"
+                                       + (" + their all-gathers)" if world > 1 else ")")},
+        "pair_scores_per_s": pair_rate,
+        "phases_ms": {k: round(v, 4) for k, v in phase_ms.items()},
+        "kernels": kernels, "roofline": roofline, "clocks": clocks,
+        "gpu_launches": launches_per_step * args.steps, "abi_calls_per_step": abi_calls // max(args.steps, 1),
+        "loss": loss_val, "setup_s": round(t_setup, 2),
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if cb is not None:
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("DL_BENCH_WORKLOAD", "c5"), choices=list(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,7 +30,8 @@ _sz = _c.c_size_t
 class DlGraph(_c.Structure):
     """Mirror of ``struct dl_graph``."""
     _fields_ = [("N", _i64), ("nnz", _i64), ("rowptr", _vp), ("col", _vp), ("perm", _vp),
-                ("n_hub", _i64), ("n_hub_items", _i64), ("hub_seg_ptr", _vp), ("item_hub", _vp)]
+                ("n_hub", _i64), ("n_hub_items", _i64), ("hub_seg_ptr", _vp), ("item_hub", _vp),
+                ("row_base", _i64)]
 
 
 _GP = _c.POINTER(DlGraph)
@@ -41,6 +42,7 @@ SIGNATURES = {
     "dl_error_string": (_c.c_char_p, [_int]),
     "dl_csr_build_workspace_bytes": (_sz, [_i64, _i64]),
     "dl_csr_build": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dl_csr_build_rect": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dl_csr_from_dense": (_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dl_rev_index": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "dl_degree_buckets_workspace_bytes": (_sz, [_i64]),
@@ -50,9 +52,12 @@ SIGNATURES = {
     "dl_edge_attn_fwd": (_int, [_GP, _vp, _int, _int, _f, _vp, _vp, _vp, _vp, _vp]),
     "dl_factor_spmm_fwd": (_int, [_GP, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp]),
     "dl_factor_bwd": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _f, _vp, _vp, _vp, _vp]),
+    "dl_factor_bwd_gather": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp, _vp]),
+    "dl_factor_bwd_edges": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp]),
     "dl_pair_score_fwd": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _f, _vp, _vp, _vp]),
     "dl_pair_incidence_workspace_bytes": (_sz, [_i64, _i64]),
     "dl_pair_incidence": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dl_pair_incidence_range": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dl_pair_score_bwd": (_int, [_GP, _vp, _vp, _vp, _vp, _int, _int, _f, _vp, _vp, _vp, _vp]),
     "dl_allpairs_score_fwd": (_int, [_vp, _vp, _i64, _int, _int, _f, _vp, _vp]),
     "dl_allpairs_score_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _int, _f, _vp, _vp, _vp]),

@@ -45,6 +45,7 @@ struct DlGraphDev {
   long long n_hub, n_hub_items;
   const long long* __restrict__ hub_seg_ptr;
   const int* __restrict__ item_hub;
+  long long row_base;
 };
 
 static inline DlGraphDev dl_graph_dev(const dl_graph* g) {
@@ -55,6 +56,7 @@ static inline DlGraphDev dl_graph_dev(const dl_graph* g) {
   o.n_hub = g->n_hub; o.n_hub_items = g->n_hub_items;
   o.hub_seg_ptr = (const long long*)g->hub_seg_ptr;
   o.item_hub = g->item_hub;
+  o.row_base = g->row_base;
   return o;
 }
 
@@ -64,12 +66,14 @@ static inline int dl_graph_ok(const dl_graph* g) {
   if (g->nnz > 0 && !g->col) return 0;
   if (g->n_hub < 0 || g->n_hub > g->N || g->n_hub_items < 0) return 0;
   if (g->n_hub > 0 && (!g->hub_seg_ptr || !g->item_hub)) return 0;
+  if (g->row_base < 0) return 0;
   return 1;
 }
 
 // One work item = one row, or one DL_SEG-edge segment of a hub row.
 struct DlItem {
-  int row;
+  int row;             // local row (indexes rowptr)
+  long long node;      // global node id = row_base + row (indexes Z, H, s, r, G, dZ)
   long long e0, e1;
   long long hub_slot;  // >= 0: partial result goes to scratch slot hub_slot; -1: direct
 };
@@ -95,6 +99,7 @@ __device__ __forceinline__ DlItem dl_decode_item(const DlGraphDev& g, long long 
     it.e1 = __ldg(g.rowptr + it.row + 1);
     it.hub_slot = -1;
   }
+  it.node = g.row_base + it.row;
   return it;
 }
 

@@ -108,7 +108,7 @@ k_factor_bwd_gather(DlGraphDev g, const float* __restrict__ Z, const float* __re
         if (M::active(lane, p))
           *reinterpret_cast<float4*>(hub_ws + it.hub_slot * D + M::offset(lane, p)) = acc[p];
     } else {
-      bwd_gather_epilogue<M>(lane, it.row, acc, Z, G, s, beta, omb, dZ, r);
+      bwd_gather_epilogue<M>(lane, it.node, acc, Z, G, s, beta, omb, dZ, r);
     }
   }
 }
@@ -137,7 +137,7 @@ k_factor_bwd_gather_hub(DlGraphDev g, const float* __restrict__ Z, const float* 
         acc[p].z = __fadd_rn(acc[p].z, v.z); acc[p].w = __fadd_rn(acc[p].w, v.w);
       }
     }
-    bwd_gather_epilogue<M>(lane, (long long)g.perm[h], acc, Z, G, s, beta, omb, dZ, r);
+    bwd_gather_epilogue<M>(lane, g.row_base + g.perm[h], acc, Z, G, s, beta, omb, dZ, r);
   }
 }
 
@@ -164,8 +164,8 @@ k_factor_bwd_edges(DlGraphDev g, const float* __restrict__ Z, const float* __res
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       const bool act = M::active(lane, p);
-      zi[p] = act ? dl_ldg4(Z + (long long)it.row * D + M::offset(lane, p)) : dl_zero4();
-      gi[p] = act ? dl_ldg4(G + (long long)it.row * D + M::offset(lane, p)) : dl_zero4();
+      zi[p] = act ? dl_ldg4(Z + it.node * D + M::offset(lane, p)) : dl_zero4();
+      gi[p] = act ? dl_ldg4(G + it.node * D + M::offset(lane, p)) : dl_zero4();
       dz[p] = dl_zero4();
     }
     for (long long base = it.e0; base < it.e1; base += 32) {
@@ -245,8 +245,8 @@ k_factor_bwd_edges(DlGraphDev g, const float* __restrict__ Z, const float* __res
         const bool valid = my_idx < cnt;
         const float sjv = __shfl_sync(DL_FULL, sj, my_idx & 31);
         const float rjv = __shfl_sync(DL_FULL, rj, my_idx & 31);
-        const float siv = __ldg(s + (long long)it.row * K + ks);
-        const float riv = __ldg(r + (long long)it.row * K + ks);
+        const float siv = __ldg(s + it.node * K + ks);
+        const float riv = __ldg(r + it.node * K + ks);
         float dws = __fadd_rn(__fdiv_rn(cij, sjv), __fdiv_rn(cji, siv));
         dws = __fsub_rn(dws, riv);
         dws = __fsub_rn(dws, rjv);
@@ -271,7 +271,7 @@ k_factor_bwd_edges(DlGraphDev g, const float* __restrict__ Z, const float* __res
       if (it.hub_slot >= 0) {
         *reinterpret_cast<float4*>(hub_ws + it.hub_slot * D + o) = dz[p];
       } else {
-        float4* dst = reinterpret_cast<float4*>(dZ + (long long)it.row * D + o);
+        float4* dst = reinterpret_cast<float4*>(dZ + it.node * D + o);
         float4 cur = *dst;
         cur.x = __fadd_rn(cur.x, dz[p].x); cur.y = __fadd_rn(cur.y, dz[p].y);
         cur.z = __fadd_rn(cur.z, dz[p].z); cur.w = __fadd_rn(cur.w, dz[p].w);
@@ -290,7 +290,7 @@ __global__ void k_bwd_edges_hub_fixup(DlGraphDev g, long long D, const float* __
     long long a = g.hub_seg_ptr[h], b = g.hub_seg_ptr[h + 1];
     float v = 0.0f;
     for (long long sg = a; sg < b; ++sg) v = __fadd_rn(v, hub_ws[sg * D + o]);
-    long long row = g.perm[h];
+    long long row = g.row_base + g.perm[h];
     dZ[row * D + o] = __fadd_rn(dZ[row * D + o], v);
   }
 }
@@ -338,7 +338,7 @@ k_factor_bwd_gather_generic(DlGraphDev g, const float* __restrict__ Z, const flo
           if (e < d) hub_ws[it.hub_slot * D + (long long)k * d + e] = acc[x];
         }
       } else {
-        const long long row = it.row;
+        const long long row = it.node;
         const float sk = __ldg(s + row * K + k);
         const float scale = __fdiv_rn(omb, sk);
         float part = 0.0f;
@@ -370,7 +370,7 @@ k_factor_bwd_gather_hub_generic(DlGraphDev g, const float* __restrict__ Z, const
   const long long D = (long long)K * d;
   for (long long h = warp0; h < g.n_hub; h += nwarps) {
     const long long a = g.hub_seg_ptr[h], b = g.hub_seg_ptr[h + 1];
-    const long long row = g.perm[h];
+    const long long row = g.row_base + g.perm[h];
     for (int k = 0; k < K; ++k) {
       const float sk = __ldg(s + row * K + k);
       const float scale = __fdiv_rn(omb, sk);
@@ -402,7 +402,7 @@ k_factor_bwd_edges_generic(DlGraphDev g, const float* __restrict__ Z, const floa
   float e[DL_MAX_K], a[DL_MAX_K];
   for (long long t = warp0; t < n_items; t += nwarps) {
     const DlItem it = dl_decode_item(g, t);
-    const long long i = it.row;
+    const long long i = it.node;
     float* acc = it.hub_slot >= 0 ? hub_ws + it.hub_slot * D : dZ + i * D;
     if (it.hub_slot >= 0) {
       for (long long x = lane; x < D; x += 32) acc[x] = 0.0f;
@@ -445,9 +445,9 @@ inline int fixup_blocks(long long n) {
 }
 
 template <class M>
-int launch_bwd(const DlGraphDev& g, long long n_items, const float* Z, const float* G,
-               const uint8_t* kstar, const float* w, const float* s, float beta, float omb, float T,
-               float* dZ, float* r, float* hub_ws, cudaStream_t st) {
+int launch_bwd_gather(const DlGraphDev& g, long long n_items, const float* Z, const float* G,
+                      const uint8_t* kstar, const float* w, const float* s, float beta, float omb,
+                      float* dZ, float* r, float* hub_ws, cudaStream_t st) {
   int grid = 1;
   int rc = dl_grid_for(k_factor_bwd_gather<M>, n_items, &grid);
   if (rc) return rc;
@@ -459,7 +459,15 @@ int launch_bwd(const DlGraphDev& g, long long n_items, const float* Z, const flo
     k_factor_bwd_gather_hub<M><<<grid, DL_CTA, 0, st>>>(g, Z, G, s, beta, omb, dZ, r, hub_ws);
     DL_LAUNCH_CHECK();
   }
-  rc = dl_grid_for(k_factor_bwd_edges<M>, n_items, &grid);
+  return DL_OK;
+}
+
+template <class M>
+int launch_bwd_edges(const DlGraphDev& g, long long n_items, const float* Z, const float* G,
+                     const uint8_t* kstar, const float* s, const float* r, float omb, float T,
+                     float* dZ, float* hub_ws, cudaStream_t st) {
+  int grid = 1;
+  int rc = dl_grid_for(k_factor_bwd_edges<M>, n_items, &grid);
   if (rc) return rc;
   k_factor_bwd_edges<M><<<grid, DL_CTA, 0, st>>>(g, Z, G, kstar, s, r, omb, T, dZ, hub_ws);
   DL_LAUNCH_CHECK();
@@ -470,21 +478,20 @@ int launch_bwd(const DlGraphDev& g, long long n_items, const float* Z, const flo
 
 extern "C" {
 
-int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const uint8_t* kstar,
-                  const float* w, const float* s, int K, int d, float beta, float one_minus_beta,
-                  float T, float* dZ, float* r, float* hub_ws, dl_stream_t stream) {
+int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
+                         const uint8_t* kstar, const float* w, const float* s, int K, int d,
+                         float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
+                         dl_stream_t stream) {
   if (!dl_graph_ok(g_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
   if (g_host->N == 0) return DL_OK;
   if (!Z || !G || !s || !dZ || !r || (g_host->nnz > 0 && (!kstar || !w))) return DL_EINVAL;
   if (g_host->n_hub_items > 0 && !hub_ws) return DL_EINVAL;
-  if (!(T == T) || T == 0.0f) return DL_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const DlGraphDev g = dl_graph_dev(g_host);
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
-  const long long D = (long long)K * d;
   int rc = -1000;
 #define BODY_MACRO(M) \
-  rc = launch_bwd<M>(g, n_items, Z, G, kstar, w, s, beta, one_minus_beta, T, dZ, r, hub_ws, st);
+  rc = launch_bwd_gather<M>(g, n_items, Z, G, kstar, w, s, beta, one_minus_beta, dZ, r, hub_ws, st);
   DL_DISPATCH_SHAPES()
 #undef BODY_MACRO
   if (rc == -1000) {
@@ -501,6 +508,31 @@ int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const 
                                                              dZ, r, hub_ws);
       DL_LAUNCH_CHECK();
     }
+    rc = DL_OK;
+  }
+  return rc;
+}
+
+int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
+                        const uint8_t* kstar, const float* s, const float* r, int K, int d,
+                        float one_minus_beta, float T, float* dZ, float* hub_ws,
+                        dl_stream_t stream) {
+  if (!dl_graph_ok(g_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
+  if (g_host->N == 0) return DL_OK;
+  if (!Z || !G || !s || !dZ || !r || (g_host->nnz > 0 && !kstar)) return DL_EINVAL;
+  if (g_host->n_hub_items > 0 && !hub_ws) return DL_EINVAL;
+  if (!(T == T) || T == 0.0f) return DL_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const DlGraphDev g = dl_graph_dev(g_host);
+  const long long n_items = g.n_hub_items + (g.N - g.n_hub);
+  const long long D = (long long)K * d;
+  int rc = -1000;
+#define BODY_MACRO(M) \
+  rc = launch_bwd_edges<M>(g, n_items, Z, G, kstar, s, r, one_minus_beta, T, dZ, hub_ws, st);
+  DL_DISPATCH_SHAPES()
+#undef BODY_MACRO
+  if (rc == -1000) {
+    int grid = 1;
     rc = dl_grid_for(k_factor_bwd_edges_generic, n_items, &grid);
     if (rc) return rc;
     k_factor_bwd_edges_generic<<<grid, DL_CTA, 0, st>>>(g, Z, G, s, r, K, d, one_minus_beta, T, dZ, hub_ws);
@@ -513,6 +545,16 @@ int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const 
     DL_LAUNCH_CHECK();
   }
   return DL_OK;
+}
+
+int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const uint8_t* kstar,
+                  const float* w, const float* s, int K, int d, float beta, float one_minus_beta,
+                  float T, float* dZ, float* r, float* hub_ws, dl_stream_t stream) {
+  if (!(T == T) || T == 0.0f) return DL_EINVAL;
+  int rc = dl_factor_bwd_gather(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, hub_ws,
+                                stream);
+  if (rc) return rc;
+  return dl_factor_bwd_edges(g_host, Z, G, kstar, s, r, K, d, one_minus_beta, T, dZ, hub_ws, stream);
 }
 
 }  // extern "C"

@@ -46,7 +46,7 @@ k_edge_attn_fwd(DlGraphDev g, const float* __restrict__ Z, float T, unsigned cha
     float sacc[NP];
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-      zi[p] = act[p] ? dl_ldg4(Z + (long long)it.row * D + off[p]) : dl_zero4();
+      zi[p] = act[p] ? dl_ldg4(Z + it.node * D + off[p]) : dl_zero4();
       sacc[p] = 0.0f;
     }
     for (long long base = it.e0; base < it.e1; base += 32) {
@@ -112,7 +112,7 @@ k_edge_attn_fwd(DlGraphDev g, const float* __restrict__ Z, float T, unsigned cha
       const int k = M::factor(lane, p);
       if (k < K && (lane % LP) == 0) {
         if (it.hub_slot >= 0) hub_ws[it.hub_slot * K + k] = v;
-        else s[(long long)it.row * K + k] = (v == 0.0f) ? 1.0f : v;
+        else s[it.node * K + k] = (v == 0.0f) ? 1.0f : v;
       }
     }
   }
@@ -134,7 +134,7 @@ k_edge_attn_fwd_generic(DlGraphDev g, const float* __restrict__ Z, int K, int d,
   for (long long t = warp0; t < n_items; t += nwarps) {
     const DlItem it = dl_decode_item(g, t);
     for (int k = 0; k < K; ++k) sacc[k] = 0.0f;
-    const float* zi = Z + (long long)it.row * D;
+    const float* zi = Z + it.node * D;
     for (long long p = it.e0; p < it.e1; ++p) {
       const float* zj = Z + (long long)__ldg(g.col + p) * D;
       int ks = dl_generic_route(zi, zj, K, d, T, lane, e, a);
@@ -145,7 +145,7 @@ k_edge_attn_fwd_generic(DlGraphDev g, const float* __restrict__ Z, int K, int d,
     if (lane == 0) {
       for (int k = 0; k < K; ++k) {
         if (it.hub_slot >= 0) hub_ws[it.hub_slot * K + k] = sacc[k];
-        else s[(long long)it.row * K + k] = (sacc[k] == 0.0f) ? 1.0f : sacc[k];
+        else s[it.node * K + k] = (sacc[k] == 0.0f) ? 1.0f : sacc[k];
       }
     }
   }
@@ -161,7 +161,7 @@ __global__ void k_attn_hub_fixup(DlGraphDev g, int K, const float* __restrict__ 
     long long a = g.hub_seg_ptr[h], b = g.hub_seg_ptr[h + 1];
     float v = 0.0f;
     for (long long sg = a; sg < b; ++sg) v = __fadd_rn(v, hub_ws[sg * K + k]);
-    s[(long long)g.perm[h] * K + k] = (v == 0.0f) ? 1.0f : v;
+    s[(g.row_base + g.perm[h]) * K + k] = (v == 0.0f) ? 1.0f : v;
   }
 }
 
@@ -226,13 +226,13 @@ k_factor_spmm_fwd(DlGraphDev g, const float* __restrict__ Z, const unsigned char
       if (it.hub_slot >= 0) {
         *reinterpret_cast<float4*>(hub_ws + it.hub_slot * D + o) = acc[p];
       } else {
-        const float4 zi = dl_ldg4(Z + (long long)it.row * D + o);
+        const float4 zi = dl_ldg4(Z + it.node * D + o);
         float4 h;
         h.x = __fadd_rn(__fmul_rn(beta, zi.x), __fmul_rn(omb, acc[p].x));
         h.y = __fadd_rn(__fmul_rn(beta, zi.y), __fmul_rn(omb, acc[p].y));
         h.z = __fadd_rn(__fmul_rn(beta, zi.z), __fmul_rn(omb, acc[p].z));
         h.w = __fadd_rn(__fmul_rn(beta, zi.w), __fmul_rn(omb, acc[p].w));
-        *reinterpret_cast<float4*>(H + (long long)it.row * D + o) = h;
+        *reinterpret_cast<float4*>(H + it.node * D + o) = h;
       }
     }
   }
@@ -252,7 +252,7 @@ k_factor_spmm_fwd_generic(DlGraphDev g, const float* __restrict__ Z,
   const long long D = (long long)K * d;
   for (long long t = warp0; t < n_items; t += nwarps) {
     const DlItem it = dl_decode_item(g, t);
-    float* acc = it.hub_slot >= 0 ? hub_ws + it.hub_slot * D : H + (long long)it.row * D;
+    float* acc = it.hub_slot >= 0 ? hub_ws + it.hub_slot * D : H + it.node * D;
     for (long long x = lane; x < D; x += 32) acc[x] = 0.0f;
     __syncwarp();
     for (long long p = it.e0; p < it.e1; ++p) {
@@ -265,7 +265,7 @@ k_factor_spmm_fwd_generic(DlGraphDev g, const float* __restrict__ Z,
     }
     __syncwarp();
     if (it.hub_slot < 0) {
-      const float* zi = Z + (long long)it.row * D;
+      const float* zi = Z + it.node * D;
       for (long long x = lane; x < D; x += 32)
         acc[x] = __fadd_rn(__fmul_rn(beta, zi[x]), __fmul_rn(omb, acc[x]));
     }
@@ -282,7 +282,7 @@ __global__ void k_spmm_hub_fixup(DlGraphDev g, long long D, const float* __restr
     long long a = g.hub_seg_ptr[h], b = g.hub_seg_ptr[h + 1];
     float v = 0.0f;
     for (long long sg = a; sg < b; ++sg) v = __fadd_rn(v, hub_ws[sg * D + o]);
-    long long row = g.perm[h];
+    long long row = g.row_base + g.perm[h];
     H[row * D + o] = __fadd_rn(__fmul_rn(beta, Z[row * D + o]), __fmul_rn(omb, v));
   }
 }

@@ -54,17 +54,21 @@ CsrWs csr_ws_layout(long long E, long long N) {
 }
 
 __global__ void k_make_keys(const long long* __restrict__ src, const long long* __restrict__ dst,
-                            long long E, long long N, int bits, unsigned long long* __restrict__ keys,
-                            int* __restrict__ status) {
+                            long long E, long long n_rows, long long n_cols, int symmetrize, int bits,
+                            unsigned long long* __restrict__ keys, int* __restrict__ status) {
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
     long long s = src[e], t = dst[e];
-    if (s < 0 || t < 0 || s >= N || t >= N) {
+    if (s < 0 || t < 0 || s >= n_rows || t >= n_cols) {
       *status = DL_ERANGE;  // benign race: every writer stores the same value
       s = 0; t = 0;
     }
-    keys[2 * e] = ((unsigned long long)s << bits) | (unsigned long long)t;
-    keys[2 * e + 1] = ((unsigned long long)t << bits) | (unsigned long long)s;
+    if (symmetrize) {
+      keys[2 * e] = ((unsigned long long)s << bits) | (unsigned long long)t;
+      keys[2 * e + 1] = ((unsigned long long)t << bits) | (unsigned long long)s;
+    } else {
+      keys[e] = ((unsigned long long)s << bits) | (unsigned long long)t;
+    }
   }
 }
 
@@ -222,27 +226,29 @@ __global__ void k_hub_item_fill(const long long* __restrict__ seg_ptr, long long
 }
 
 // ---- pair incidence ---------------------------------------------------------------------------
+// key = local row of the endpoint if it lies in [row_lo, row_hi), else the sentinel n_local (sorts
+// last and is dropped by the decode kernel)
 __global__ void k_incidence_keys(const int* __restrict__ u, const int* __restrict__ v, long long P,
-                                 long long N, unsigned* __restrict__ key, unsigned* __restrict__ val,
-                                 int* __restrict__ status) {
+                                 long long row_lo, long long row_hi, unsigned* __restrict__ key,
+                                 unsigned* __restrict__ val) {
   long long stride = (long long)gridDim.x * blockDim.x;
+  const unsigned sentinel = (unsigned)(row_hi - row_lo);
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += stride) {
-    int a = u[p], b = v[p];
-    if (a < 0 || b < 0 || a >= N || b >= N) {
-      if (status) *status = DL_ERANGE;
-      a = 0; b = 0;
-    }
-    key[2 * p] = (unsigned)a;     val[2 * p] = (unsigned)(2 * p);
-    key[2 * p + 1] = (unsigned)b; val[2 * p + 1] = (unsigned)(2 * p + 1);
+    long long a = u[p], b = v[p];
+    key[2 * p] = (a >= row_lo && a < row_hi) ? (unsigned)(a - row_lo) : sentinel;
+    val[2 * p] = (unsigned)(2 * p);
+    key[2 * p + 1] = (b >= row_lo && b < row_hi) ? (unsigned)(b - row_lo) : sentinel;
+    val[2 * p + 1] = (unsigned)(2 * p + 1);
   }
 }
 
 __global__ void k_incidence_decode(const unsigned* __restrict__ skey, const unsigned* __restrict__ sval,
                                    const int* __restrict__ u, const int* __restrict__ v, long long M,
-                                   int* __restrict__ other, int* __restrict__ pair,
+                                   unsigned sentinel, int* __restrict__ other, int* __restrict__ pair,
                                    long long* __restrict__ marks) {
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < M; t += stride) {
+    if (skey[t] >= sentinel) continue;
     unsigned x = sval[t];
     long long p = x >> 1;
     other[t] = (x & 1u) ? u[p] : v[p];
@@ -273,7 +279,17 @@ size_t dl_csr_build_workspace_bytes(int64_t E, int64_t N) {
 int dl_csr_build(const int64_t* src, const int64_t* dst, int64_t E, int64_t N, int64_t* rowptr,
                  int32_t* col, int64_t* nnz_out, int32_t* status_out, void* ws, size_t ws_bytes,
                  dl_stream_t stream) {
-  if (E < 0 || N < 0 || N >= (1LL << 31) || !rowptr || !nnz_out || !status_out || !ws) return DL_EINVAL;
+  return dl_csr_build_rect(src, dst, E, N, N, 1, rowptr, col, nnz_out, status_out, ws, ws_bytes, stream);
+}
+
+int dl_csr_build_rect(const int64_t* src, const int64_t* dst, int64_t E, int64_t n_rows,
+                      int64_t n_cols, int symmetrize, int64_t* rowptr, int32_t* col,
+                      int64_t* nnz_out, int32_t* status_out, void* ws, size_t ws_bytes,
+                      dl_stream_t stream) {
+  const int64_t N = n_rows;
+  if (E < 0 || n_rows < 0 || n_cols < 0 || n_rows >= (1LL << 31) || n_cols >= (1LL << 31)) return DL_EINVAL;
+  if (symmetrize && n_rows != n_cols) return DL_EINVAL;
+  if (!rowptr || !nnz_out || !status_out || !ws) return DL_EINVAL;
   if (E > 0 && (!src || !dst || !col)) return DL_EINVAL;
   if (E >= (1LL << 61)) return DL_EINVAL;
   CsrWs L = csr_ws_layout(E, N);
@@ -285,17 +301,18 @@ int dl_csr_build(const int64_t* src, const int64_t* dst, int64_t E, int64_t N, i
   long long* marks = (long long*)(base + L.marks);
   void* cub_ws = base + L.cub;
   size_t cub_bytes = L.cub_bytes;
-  const long long M = 2 * E;
-  const int bits = dl_bits_for(N > 1 ? N : 2);
+  const long long M = symmetrize ? 2 * E : E;
+  const int bits = dl_bits_for(n_cols > 1 ? n_cols : 2);
+  const int row_bits = dl_bits_for(n_rows > 1 ? n_rows : 2);
 
   DL_CUDA_TRY(cudaMemsetAsync(status_out, 0, sizeof(int32_t), st));
   DL_CUDA_TRY(cudaMemsetAsync(nnz_out, 0, sizeof(int64_t), st));
   DL_CUDA_TRY(cudaMemsetAsync(marks, 0, (size_t)(N + 1) * 8, st));
   if (M > 0) {
-    k_make_keys<<<blocks_for(E), 256, 0, st>>>((const long long*)src, (const long long*)dst, E, N,
-                                               bits, ka, status_out);
+    k_make_keys<<<blocks_for(E), 256, 0, st>>>((const long long*)src, (const long long*)dst, E, n_rows,
+                                               n_cols, symmetrize, bits, ka, status_out);
     DL_LAUNCH_CHECK();
-    DL_CUDA_TRY(cub::DeviceRadixSort::SortKeys(cub_ws, cub_bytes, ka, kb, M, 0, 2 * bits, st));
+    DL_CUDA_TRY(cub::DeviceRadixSort::SortKeys(cub_ws, cub_bytes, ka, kb, M, 0, bits + row_bits, st));
     DL_CUDA_TRY(cub::DeviceSelect::Unique(cub_ws, cub_bytes, kb, ka, (long long*)nnz_out, M, st));
     k_decode_keys<<<blocks_for(M), 256, 0, st>>>(ka, (const long long*)nnz_out, bits, col, marks);
     DL_LAUNCH_CHECK();
@@ -418,7 +435,15 @@ size_t dl_pair_incidence_workspace_bytes(int64_t P, int64_t N) {
 int dl_pair_incidence(const int32_t* u, const int32_t* v, int64_t P, int64_t N, int64_t* inc_ptr,
                       int32_t* inc_other, int32_t* inc_pair, void* ws, size_t ws_bytes,
                       dl_stream_t stream) {
-  if (P < 0 || N < 0 || P >= (1LL << 30) || !inc_ptr || !ws) return DL_EINVAL;
+  return dl_pair_incidence_range(u, v, P, 0, N, inc_ptr, inc_other, inc_pair, ws, ws_bytes, stream);
+}
+
+int dl_pair_incidence_range(const int32_t* u, const int32_t* v, int64_t P, int64_t row_lo,
+                            int64_t row_hi, int64_t* inc_ptr, int32_t* inc_other, int32_t* inc_pair,
+                            void* ws, size_t ws_bytes, dl_stream_t stream) {
+  const int64_t N = row_hi - row_lo;
+  if (row_lo < 0 || N < 0 || N >= (1LL << 31) - 1) return DL_EINVAL;
+  if (P < 0 || P >= (1LL << 30) || !inc_ptr || !ws) return DL_EINVAL;
   if (P > 0 && (!u || !v || !inc_other || !inc_pair)) return DL_EINVAL;
   if (ws_bytes < dl_pair_incidence_workspace_bytes(P, N)) return DL_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -434,12 +459,13 @@ int dl_pair_incidence(const int32_t* u, const int32_t* v, int64_t P, int64_t N, 
   size_t cub_bytes = align256(incidence_cub_bytes(M, N));
   DL_CUDA_TRY(cudaMemsetAsync(marks, 0, (size_t)(N + 1) * 8, st));
   if (M > 0) {
-    k_incidence_keys<<<blocks_for(P), 256, 0, st>>>(u, v, P, N, key_in, val_in, nullptr);
+    k_incidence_keys<<<blocks_for(P), 256, 0, st>>>(u, v, P, row_lo, row_hi, key_in, val_in);
     DL_LAUNCH_CHECK();
-    const int bits = dl_bits_for(N > 1 ? N : 2);
+    const int bits = dl_bits_for(N + 1 > 1 ? N + 1 : 2);
     DL_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, key_in, key_out, val_in, val_out,
                                                 M, 0, bits, st));
-    k_incidence_decode<<<blocks_for(M), 256, 0, st>>>(key_out, val_out, u, v, M, inc_other, inc_pair, marks);
+    k_incidence_decode<<<blocks_for(M), 256, 0, st>>>(key_out, val_out, u, v, M, (unsigned)N, inc_other,
+                                                      inc_pair, marks);
     DL_LAUNCH_CHECK();
   }
   DL_CUDA_TRY(cub::DeviceScan::InclusiveScan(cub_ws, cub_bytes, marks, (long long*)inc_ptr,

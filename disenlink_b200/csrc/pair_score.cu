@@ -129,8 +129,8 @@ k_pair_score_bwd(DlGraphDev g, const int* __restrict__ inc_pair, const float* __
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       const bool act = M::active(lane, p);
-      zn[p] = act ? dl_ldg4(Z + (long long)it.row * D + M::offset(lane, p)) : dl_zero4();
-      hn[p] = act ? dl_ldg4(H + (long long)it.row * D + M::offset(lane, p)) : dl_zero4();
+      zn[p] = act ? dl_ldg4(Z + it.node * D + M::offset(lane, p)) : dl_zero4();
+      hn[p] = act ? dl_ldg4(H + it.node * D + M::offset(lane, p)) : dl_zero4();
       az[p] = dl_zero4();
       ah[p] = dl_zero4();
     }
@@ -192,8 +192,8 @@ k_pair_score_bwd(DlGraphDev g, const int* __restrict__ inc_pair, const float* __
         *reinterpret_cast<float4*>(hub_ws + it.hub_slot * 2 * D + o) = az[p];
         *reinterpret_cast<float4*>(hub_ws + it.hub_slot * 2 * D + D + o) = ah[p];
       } else {
-        *reinterpret_cast<float4*>(dZ + (long long)it.row * D + o) = az[p];
-        *reinterpret_cast<float4*>(dH + (long long)it.row * D + o) = ah[p];
+        *reinterpret_cast<float4*>(dZ + it.node * D + o) = az[p];
+        *reinterpret_cast<float4*>(dH + it.node * D + o) = ah[p];
       }
     }
   }
@@ -211,12 +211,12 @@ k_pair_score_bwd_generic(DlGraphDev g, const int* __restrict__ inc_pair, const f
   const long long D = (long long)K * d;
   for (long long t = warp0; t < n_items; t += nwarps) {
     const DlItem it = dl_decode_item(g, t);
-    float* az = it.hub_slot >= 0 ? hub_ws + it.hub_slot * 2 * D : dZ + (long long)it.row * D;
-    float* ah = it.hub_slot >= 0 ? hub_ws + it.hub_slot * 2 * D + D : dH + (long long)it.row * D;
+    float* az = it.hub_slot >= 0 ? hub_ws + it.hub_slot * 2 * D : dZ + it.node * D;
+    float* ah = it.hub_slot >= 0 ? hub_ws + it.hub_slot * 2 * D + D : dH + it.node * D;
     for (long long x = lane; x < D; x += 32) { az[x] = 0.0f; ah[x] = 0.0f; }
     __syncwarp();
-    const float* zn = Z + (long long)it.row * D;
-    const float* hn = H + (long long)it.row * D;
+    const float* zn = Z + it.node * D;
+    const float* hn = H + it.node * D;
     for (long long e = it.e0; e < it.e1; ++e) {
       const long long o = __ldg(g.col + e);
       const float ds = __ldg(dS + __ldg(inc_pair + e));
@@ -249,7 +249,7 @@ __global__ void k_pair_bwd_hub_fixup(DlGraphDev g, long long D, const float* __r
       vz = __fadd_rn(vz, hub_ws[sg * 2 * D + o]);
       vh = __fadd_rn(vh, hub_ws[sg * 2 * D + D + o]);
     }
-    long long row = g.perm[h];
+    long long row = g.row_base + g.perm[h];
     dZ[row * D + o] = vz;
     dH[row * D + o] = vh;
   }

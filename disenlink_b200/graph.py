@@ -27,11 +27,14 @@ class Graph:
     warp owns more than one segment.
     """
 
-    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, n_nodes: int):
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, n_nodes: int, row_base: int = 0,
+                 n_global: int = None):
         require_cuda(rowptr, "rowptr")
         assert rowptr.dtype == torch.int64 and col.dtype == torch.int32
         self.device = rowptr.device
-        self.N = int(n_nodes)
+        self.N = int(n_nodes)                 # rows held here
+        self.row_base = int(row_base)         # global id of local row 0 (node-partitioned runs)
+        self.n_global = int(n_global) if n_global is not None else self.N
         self.rowptr = rowptr.contiguous()
         self.col = col.contiguous()
         self.nnz = int(col.numel())
@@ -125,7 +128,7 @@ class Graph:
                                      stream_of(dev)), "dl_hub_items(fill)")
         self.struct = DlGraph(self.N, self.nnz, ptr(self.rowptr), ptr(self.col), ptr(self.perm),
                               self.n_hub, self.n_hub_items, ptr(self.hub_seg_ptr),
-                              ptr(self.item_hub))
+                              ptr(self.item_hub), self.row_base)
         self._hub_ws = None
 
     @property

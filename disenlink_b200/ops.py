@@ -38,27 +38,31 @@ def _check_Z(Z: torch.Tensor, n_nodes: int):
 # --------------------------------------------------------------------------------------------
 # raw kernel wrappers (no autograd)
 # --------------------------------------------------------------------------------------------
-def edge_attn_fwd(graph: Graph, Z: torch.Tensor, T: float = 1.0):
-    """-> (kstar u8 [nnz], w f32 [nnz], s f32 [N,K]).  [ref: model.py:56-73]"""
-    K, d = _check_Z(Z, graph.N)
+def edge_attn_fwd(graph: Graph, Z: torch.Tensor, T: float = 1.0, out=None):
+    """-> (kstar u8 [nnz], w f32 [nnz], s f32 [N,K]).  [ref: model.py:56-73]
+    `out` = optional preallocated (kstar, w, s)."""
+    K, d = _check_Z(Z, graph.n_global)
     Z = Z.contiguous()
     dev = Z.device
     with torch.cuda.device(dev):
-        kstar = torch.empty(max(graph.nnz, 1), dtype=torch.uint8, device=dev)
-        w = torch.empty(max(graph.nnz, 1), dtype=torch.float32, device=dev)
-        s = torch.empty(graph.N, K, dtype=torch.float32, device=dev)
+        if out is not None:
+            kstar, w, s = out
+        else:
+            kstar = torch.empty(max(graph.nnz, 1), dtype=torch.uint8, device=dev)
+            w = torch.empty(max(graph.nnz, 1), dtype=torch.float32, device=dev)
+            s = torch.empty(graph.n_global, K, dtype=torch.float32, device=dev)
         check(lib().dl_edge_attn_fwd(graph.ref, ptr(Z), K, d, float(T), ptr(kstar), ptr(w), ptr(s),
                                      ptr(graph.hub_scratch(K)), stream_of(dev)), "dl_edge_attn_fwd")
     return kstar[:graph.nnz], w[:graph.nnz], s
 
 
-def factor_spmm_fwd(graph: Graph, Z, kstar, w, s, beta: float):
+def factor_spmm_fwd(graph: Graph, Z, kstar, w, s, beta: float, out=None):
     """-> H [N,K,d].  [ref: model.py:75]"""
-    K, d = _check_Z(Z, graph.N)
+    K, d = _check_Z(Z, graph.n_global)
     Z = Z.contiguous()
     dev = Z.device
     with torch.cuda.device(dev):
-        H = torch.empty_like(Z)
+        H = torch.empty_like(Z) if out is None else out
         check(lib().dl_factor_spmm_fwd(graph.ref, ptr(Z), ptr(kstar), ptr(w), ptr(s), K, d,
                                        float(beta), one_minus(beta), ptr(H),
                                        ptr(graph.hub_scratch(K * d)), stream_of(dev)),
@@ -66,17 +70,40 @@ def factor_spmm_fwd(graph: Graph, Z, kstar, w, s, beta: float):
     return H
 
 
-def factor_bwd(graph: Graph, Z, G, kstar, w, s, beta: float, T: float = 1.0, dZ=None):
+def factor_bwd_gather(graph: Graph, Z, G, kstar, w, s, beta: float, dZ, r):
+    """Pass 1 of the backward: r [N,K] and dZ += beta*G + T_ (see csrc/factor_bwd.cu)."""
+    K, d = _check_Z(Z, graph.n_global)
+    dev = Z.device
+    with torch.cuda.device(dev):
+        check(lib().dl_factor_bwd_gather(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d,
+                                         float(beta), one_minus(beta), ptr(dZ), ptr(r),
+                                         ptr(graph.hub_scratch(K * d)), stream_of(dev)),
+              "dl_factor_bwd_gather")
+
+
+def factor_bwd_edges(graph: Graph, Z, G, kstar, s, r, beta: float, T: float, dZ):
+    """Pass 2 of the backward: dZ += attention-weight terms (needs r of every neighbour)."""
+    K, d = _check_Z(Z, graph.n_global)
+    dev = Z.device
+    with torch.cuda.device(dev):
+        check(lib().dl_factor_bwd_edges(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(s), ptr(r), K, d,
+                                        one_minus(beta), float(T), ptr(dZ),
+                                        ptr(graph.hub_scratch(K * d)), stream_of(dev)),
+              "dl_factor_bwd_edges")
+
+
+def factor_bwd(graph: Graph, Z, G, kstar, w, s, beta: float, T: float = 1.0, dZ=None, r=None):
     """dL/dZ through attention + aggregation given G = dL/dH; accumulated into dZ if given.
     -> (dZ, r).  [ref: autograd of model.py:56-75]"""
-    K, d = _check_Z(Z, graph.N)
+    K, d = _check_Z(Z, graph.n_global)
     Z = Z.contiguous()
     G = G.contiguous()
     dev = Z.device
     with torch.cuda.device(dev):
         if dZ is None:
             dZ = torch.zeros_like(Z)
-        r = torch.empty(graph.N, K, dtype=torch.float32, device=dev)
+        if r is None:
+            r = torch.empty(graph.n_global, K, dtype=torch.float32, device=dev)
         check(lib().dl_factor_bwd(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d,
                                   float(beta), one_minus(beta), float(T), ptr(dZ), ptr(r),
                                   ptr(graph.hub_scratch(K * d)), stream_of(dev)), "dl_factor_bwd")
@@ -129,22 +156,27 @@ class PairBatch:
         return self._inc
 
 
-def pair_score_fwd(Z, H, batch: PairBatch, T: float = 1.0, want_logit=True, want_prob=True):
+def pair_score_fwd(Z, H, batch: PairBatch, T: float = 1.0, want_logit=True, want_prob=True, out=None):
+    """-> (logit [P] or None, prob [P] or None).  `out` = optional preallocated (logit, prob)."""
     K, d = _check_Z(Z, batch.N)
     Z = Z.contiguous()
     H = H.contiguous()
     dev = Z.device
     with torch.cuda.device(dev):
-        logit = torch.empty(max(batch.P, 1), dtype=torch.float32, device=dev) if want_logit else None
-        prob = torch.empty(max(batch.P, 1), dtype=torch.float32, device=dev) if want_prob else None
+        if out is not None:
+            logit, prob = out
+            want_logit, want_prob = logit is not None, prob is not None
+        else:
+            logit = torch.empty(max(batch.P, 1), dtype=torch.float32, device=dev) if want_logit else None
+            prob = torch.empty(max(batch.P, 1), dtype=torch.float32, device=dev) if want_prob else None
         check(lib().dl_pair_score_fwd(ptr(batch.u), ptr(batch.v), batch.P, ptr(Z), ptr(H), batch.N,
                                       K, d, float(T), ptr(logit), ptr(prob), stream_of(dev)),
               "dl_pair_score_fwd")
     return (logit[:batch.P] if want_logit else None), (prob[:batch.P] if want_prob else None)
 
 
-def pair_score_bwd(Z, H, batch: PairBatch, dS, T: float = 1.0):
-    """-> (dZ, dH) of the decoder given dS = dL/dlogit."""
+def pair_score_bwd(Z, H, batch: PairBatch, dS, T: float = 1.0, out=None):
+    """-> (dZ, dH) of the decoder given dS = dL/dlogit.  `out` = optional preallocated (dZ, dH)."""
     K, d = _check_Z(Z, batch.N)
     Z = Z.contiguous()
     H = H.contiguous()
@@ -152,8 +184,7 @@ def pair_score_bwd(Z, H, batch: PairBatch, dS, T: float = 1.0):
     dev = Z.device
     g, inc_pair = batch.incidence()
     with torch.cuda.device(dev):
-        dZ = torch.empty_like(Z)
-        dH = torch.empty_like(Z)
+        dZ, dH = out if out is not None else (torch.empty_like(Z), torch.empty_like(Z))
         check(lib().dl_pair_score_bwd(g.ref, ptr(inc_pair), ptr(Z), ptr(H), ptr(dS), K, d, float(T),
                                       ptr(dZ), ptr(dH), ptr(g.hub_scratch(2 * K * d)),
                                       stream_of(dev)), "dl_pair_score_bwd")
@@ -213,6 +244,58 @@ def pair_score(Z, H, batch: PairBatch, T: float = 1.0, as_prob: bool = True):
     """sigmoid(sum_k exp(z_u^k.z_v^k/T) (h_u^k.h_v^k)) (or the logit) for every pair of the batch.
     Differentiable w.r.t. Z and H.  [ref: model.py:109-113]"""
     return _PairScore.apply(Z, H, batch, T, as_prob)
+
+
+class _LinkBCELoss(torch.autograd.Function):
+    """Whole hot path as one differentiable op with explicit buffer reuse (4 [N,K,d] buffers live):
+    attention -> aggregation -> pair scores -> weighted BCE -> decoder backward -> factor backward.
+    [ref: model.py:105-114 + main_disentangled.py:195 and its autograd]"""
+
+    @staticmethod
+    def forward(ctx, Z, graph, batch, labels, weights, beta, T):
+        Zc = Z.detach().contiguous()
+        kstar, w, s = edge_attn_fwd(graph, Zc, T)
+        H = factor_spmm_fwd(graph, Zc, kstar, w, s, beta)
+        _, prob = pair_score_fwd(Zc, H, batch, T, want_logit=False)
+        with torch.enable_grad():
+            p = prob.detach().requires_grad_(True)
+            # torch's own BCE (log clamped at -100, backward clamped at 1e-12) keeps the script's
+            # numerics; weights fold the means and the 1/m of main_disentangled.py:195
+            loss = (torch.nn.functional.binary_cross_entropy(p, labels, reduction="none") * weights).sum()
+            need_grad = ctx.needs_input_grad[0]
+            dprob = torch.autograd.grad(loss, p)[0] if need_grad else None
+        if need_grad:
+            dS = dprob * (1.0 - prob) * prob
+            dZ, dH = pair_score_bwd(Zc, H, batch, dS, T)
+            factor_bwd(graph, Zc, dH, kstar, w, s, beta, T, dZ=dZ)
+            ctx.save_for_backward(dZ)
+        ctx.mark_non_differentiable(prob, H)
+        return loss.detach(), prob, H
+
+    @staticmethod
+    def backward(ctx, gloss, _gp, _gh):
+        (dZ,) = ctx.saved_tensors
+        return dZ.mul_(gloss), None, None, None, None, None, None   # in place: dZ is this op's own buffer
+
+
+def link_bce_loss(Z, graph: Graph, batch: PairBatch, labels, weights, beta: float, T: float = 1.0):
+    """sum_p weights[p] * BCE(score(u_p, v_p), labels[p]) with score as in model.py:113.
+    -> (loss, prob [P], H [N,K,d]); differentiable w.r.t. Z only through `loss`."""
+    return _LinkBCELoss.apply(Z, graph, batch, labels, weights, beta, T)
+
+
+def pairs_exactly_once(u, v, n_nodes: int):
+    """Row-major sorted pairs that occur exactly once: the `mask == 1` selection of the script's
+    summed dense masks (main_disentangled.py:175-178,195).  Integer work on the device."""
+    key, cnt = torch.unique(u.to(torch.int64) * n_nodes + v.to(torch.int64), return_counts=True)
+    key = key[cnt == 1]
+    return key // n_nodes, key % n_nodes
+
+
+def pairs_at_least_once(u, v, n_nodes: int):
+    """Row-major sorted unique pairs: the clamped eval masks (main_disentangled.py:188-190)."""
+    key = torch.unique(u.to(torch.int64) * n_nodes + v.to(torch.int64))
+    return key // n_nodes, key % n_nodes
 
 
 class _AllPairsScore(torch.autograd.Function):

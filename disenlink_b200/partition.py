@@ -1,0 +1,261 @@
+"""Node-partitioned execution of the hot path across the GPUs of one node (NCCL over NVLink).
+
+The reference is single-process; for graphs that do not fit one device the
+nodes are split into `world` equal contiguous ranges.  Rank r owns rows [lo, hi) of the symmetric
+CSR (columns stay global), their Z / H / s / r / dZ rows and an equal share of every pair batch.
+Per-node arrays are allocated full size ([n_pad, ...], n_pad = world * ceil(N / world)); a kernel
+call reads any gathered row and writes only the owned slice (dl_graph.row_base), and the slice is
+then exchanged IN PLACE with one all-gather -- no reductions, no atomics, owner computes.  Per
+step (forward + backward) the exchange steps are
+
+    all-gather Z -> attention -> all-gather s -> aggregation -> all-gather H -> pair scores
+    -> all-gather prob -> decoder backward (owned nodes, all incident pairs) -> all-gather dH
+    -> backward pass 1 -> all-gather r -> backward pass 2
+
+Each row's result is produced by the same kernel code walking the same column-sorted row as on one
+GPU, so the partitioned result equals the single-GPU result bit for bit.
+
+The orchestration below is backend-agnostic: the product backend (`CudaBackend`) calls the CUDA
+kernels; tests inject a CPU backend to exercise partition bounds, padding, pair sharding and the
+exchange sequence over gloo with world_size 2.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class NodePartition:
+    n_global: int
+    world: int
+    rank: int
+
+    @property
+    def per(self) -> int:
+        return (self.n_global + self.world - 1) // self.world
+
+    @property
+    def n_pad(self) -> int:
+        return self.per * self.world
+
+    @property
+    def lo(self) -> int:
+        return min(self.rank * self.per, self.n_global)
+
+    @property
+    def hi(self) -> int:
+        return min(self.lo + self.per, self.n_global)
+
+    @property
+    def n_local(self) -> int:
+        return self.hi - self.lo
+
+    def owner_of(self, node: torch.Tensor) -> torch.Tensor:
+        return torch.div(node, self.per, rounding_mode="floor")
+
+
+def owned_entries(src: torch.Tensor, dst: torch.Tensor, part: NodePartition):
+    """Directed (local_row, global_col) entries of the symmetrised adjacency whose row this rank
+    owns: (s,t) if s is owned, (t,s) if t is owned (duplicates are collapsed by the CSR build).
+    [ref: main_disentangled.py:141  adj_sym = adj + adj.t()]"""
+    ms = (src >= part.lo) & (src < part.hi)
+    mt = (dst >= part.lo) & (dst < part.hi)
+    rows = torch.cat([src[ms], dst[mt]]) - part.lo
+    cols = torch.cat([dst[ms], src[mt]])
+    return rows, cols
+
+
+def pair_shard(P: int, world: int, rank: int):
+    """Contiguous equal share of a pair batch (padded length per rank, [p_lo, p_hi))."""
+    per = (P + world - 1) // world
+    lo = min(rank * per, P)
+    return per, lo, min(lo + per, P)
+
+
+def all_gather_rows(full: torch.Tensor, part: NodePartition, group=None) -> None:
+    """In-place all-gather of the owned row block of a full-size [n_pad, ...] array."""
+    if part.world == 1:
+        return
+    mine = full[part.rank * part.per:(part.rank + 1) * part.per]
+    dist.all_gather_into_tensor(full, mine, group=group)
+
+
+def all_gather_flat(full: torch.Tensor, per: int, rank: int, world: int, group=None) -> None:
+    if world == 1:
+        return
+    dist.all_gather_into_tensor(full, full[rank * per:(rank + 1) * per], group=group)
+
+
+class CudaBackend:
+    """The product backend: every call goes to libdisenlink_b200.so."""
+
+    def __init__(self):
+        from . import ops
+        from .graph import Graph
+        self.ops, self.Graph = ops, Graph
+
+    def build_graph(self, src, dst, part: NodePartition):
+        from ._lib import check, lib, ptr, stream_of
+        rows, cols = owned_entries(src, dst, part)
+        dev = src.device
+        E = int(rows.numel())
+        L = lib()
+        with torch.cuda.device(dev):
+            rowptr = torch.empty(part.n_local + 1, dtype=torch.int64, device=dev)
+            col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+            meta = torch.zeros(2, dtype=torch.int64, device=dev)
+            ws_bytes = L.dl_csr_build_workspace_bytes(E, part.n_local)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            check(L.dl_csr_build_rect(ptr(rows.contiguous()), ptr(cols.contiguous()), E, part.n_local,
+                                      part.n_global, 0, ptr(rowptr), ptr(col), ptr(meta),
+                                      meta[1:].data_ptr(), ptr(ws), ws_bytes, stream_of(dev)),
+                  "dl_csr_build_rect")
+            nnz = int(meta[0].item())
+            del ws
+            col = col[:nnz].clone()
+        return self.Graph(rowptr, col, part.n_local, row_base=part.lo, n_global=part.n_pad)
+
+    def build_pairs(self, u, v, part: NodePartition):
+        """-> (local shard PairBatch for scoring, incidence graph of owned nodes over ALL pairs,
+        inc_pair)."""
+        from ._lib import check, lib, ptr, stream_of
+        ops = self.ops
+        P = int(u.numel())
+        per, p_lo, p_hi = pair_shard(P, part.world, part.rank)
+        shard = ops.PairBatch(u[p_lo:p_hi], v[p_lo:p_hi], part.n_pad)
+        dev = u.device
+        u32, v32 = u.to(torch.int32).contiguous(), v.to(torch.int32).contiguous()
+        L = lib()
+        with torch.cuda.device(dev):
+            inc_ptr = torch.empty(part.n_local + 1, dtype=torch.int64, device=dev)
+            inc_other = torch.empty(max(2 * P, 1), dtype=torch.int32, device=dev)
+            inc_pair = torch.empty(max(2 * P, 1), dtype=torch.int32, device=dev)
+            ws_bytes = L.dl_pair_incidence_workspace_bytes(P, part.n_local + 1)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            check(L.dl_pair_incidence_range(ptr(u32), ptr(v32), P, part.lo, part.hi, ptr(inc_ptr),
+                                            ptr(inc_other), ptr(inc_pair), ptr(ws), ws_bytes,
+                                            stream_of(dev)), "dl_pair_incidence_range")
+            m = int(inc_ptr[-1].item())
+            del ws
+            inc_other, inc_pair = inc_other[:m].clone(), inc_pair[:m].clone()
+        inc = self.Graph(inc_ptr, inc_other, part.n_local, row_base=part.lo, n_global=part.n_pad)
+        return shard, inc, inc_pair
+
+    # -- kernels (all write only the owned rows of the full-size outputs) --
+    def edge_attn_fwd(self, g, Z, T, kstar, w, s):
+        self.ops.edge_attn_fwd(g, Z, T, out=(kstar, w, s))
+
+    def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H):
+        self.ops.factor_spmm_fwd(g, Z, kstar, w, s, beta, out=H)
+
+    def pair_score_fwd(self, Z, H, shard, T, prob_slice):
+        self.ops.pair_score_fwd(Z, H, shard, T, out=(None, prob_slice))
+
+    def pair_score_bwd(self, inc, inc_pair, Z, H, dS, T, dZ, dH):
+        from ._lib import check, lib, ptr, stream_of
+        K, d = int(Z.shape[1]), int(Z.shape[2])
+        dev = Z.device
+        with torch.cuda.device(dev):
+            check(lib().dl_pair_score_bwd(inc.ref, ptr(inc_pair), ptr(Z), ptr(H), ptr(dS), K, d, float(T),
+                                          ptr(dZ), ptr(dH), ptr(inc.hub_scratch(2 * K * d)),
+                                          stream_of(dev)), "dl_pair_score_bwd")
+
+    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r):
+        self.ops.factor_bwd_gather(g, Z, G, kstar, w, s, beta, dZ, r)
+
+    def factor_bwd_edges(self, g, Z, G, kstar, s, r, beta, T, dZ):
+        self.ops.factor_bwd_edges(g, Z, G, kstar, s, r, beta, T, dZ)
+
+
+class PartitionedLinkStep:
+    """One forward+backward pass of the hot path on a node-partitioned graph.
+
+    Buffers are allocated once; `run(Z_full)` expects the owned rows of Z_full to hold this rank's
+    factor embeddings and leaves dL/dZ of the owned rows in `self.dZ[lo:hi]`."""
+
+    def __init__(self, src, dst, n_global, u, v, labels, weights, K, d, beta, T,
+                 world=1, rank=0, group=None, backend=None, device=None, mark=None):
+        self.mark = mark if mark is not None else (lambda name: None)  # phase boundary hook (bench)
+        self.part = NodePartition(int(n_global), int(world), int(rank))
+        self.group = group
+        self.be = backend if backend is not None else CudaBackend()
+        self.K, self.d, self.beta, self.T = int(K), int(d), float(beta), float(T)
+        dev = device if device is not None else src.device
+        self.device = dev
+        part = self.part
+        self.graph = self.be.build_graph(src, dst, part)
+        self.P = int(u.numel())
+        self.p_per, self.p_lo, self.p_hi = pair_shard(self.P, part.world, part.rank)
+        self.shard, self.inc, self.inc_pair = self.be.build_pairs(u, v, part)
+        P_pad = self.p_per * part.world
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.labels = torch.zeros(P_pad, **f32)
+        self.labels[:self.P] = labels
+        self.weights = torch.zeros(P_pad, **f32)
+        self.weights[:self.P] = weights
+        nnz = self.graph.nnz
+        self.kstar = torch.empty(max(nnz, 1), dtype=torch.uint8, device=dev)
+        self.w = torch.empty(max(nnz, 1), **f32)
+        self.s = torch.ones(part.n_pad, K, **f32)
+        self.r = torch.zeros(part.n_pad, K, **f32)
+        self.H = torch.zeros(part.n_pad, K, d, **f32)
+        self.dZ = torch.zeros(part.n_pad, K, d, **f32)
+        self.dH = torch.zeros(part.n_pad, K, d, **f32)
+        self.prob = torch.zeros(P_pad, **f32)
+        self.dS = torch.zeros(P_pad, **f32)
+        self.loss = None
+
+    def forward(self, Z):
+        part, be, g, mark = self.part, self.be, self.graph, self.mark
+        mark("begin")
+        all_gather_rows(Z, part, self.group)
+        mark("ag_Z")
+        be.edge_attn_fwd(g, Z, self.T, self.kstar, self.w, self.s)
+        mark("attn_fwd")
+        all_gather_rows(self.s, part, self.group)
+        mark("ag_s")
+        be.factor_spmm_fwd(g, Z, self.kstar, self.w, self.s, self.beta, self.H)
+        mark("spmm_fwd")
+        all_gather_rows(self.H, part, self.group)
+        mark("ag_H")
+        lo = part.rank * self.p_per
+        if self.p_hi > self.p_lo:
+            be.pair_score_fwd(Z, self.H, self.shard, self.T, self.prob[lo:lo + (self.p_hi - self.p_lo)])
+        mark("pair_fwd")
+        all_gather_flat(self.prob, self.p_per, part.rank, part.world, self.group)
+        mark("ag_prob")
+        return self.H, self.prob
+
+    def loss_and_grad_logit(self):
+        """weighted BCE over all pairs and dL/dlogit (every rank evaluates the full P-vector; it
+        is P floats).  d/dlogit of BCE(sigmoid(S), y) = (p - y)."""
+        p = self.prob
+        eps = 1e-12
+        self.loss = -(self.weights * (self.labels * torch.log(p.clamp_min(eps)) +
+                                      (1 - self.labels) * torch.log((1 - p).clamp_min(eps)))).sum()
+        torch.sub(p, self.labels, out=self.dS)
+        self.dS.mul_(self.weights)
+        self.mark("loss")
+        return self.loss
+
+    def backward(self, Z):
+        part, be, g, mark = self.part, self.be, self.graph, self.mark
+        be.pair_score_bwd(self.inc, self.inc_pair, Z, self.H, self.dS, self.T, self.dZ, self.dH)
+        mark("pair_bwd")
+        all_gather_rows(self.dH, part, self.group)
+        mark("ag_dH")
+        be.factor_bwd_gather(g, Z, self.dH, self.kstar, self.w, self.s, self.beta, self.dZ, self.r)
+        mark("bwd_gather")
+        all_gather_rows(self.r, part, self.group)
+        mark("ag_r")
+        be.factor_bwd_edges(g, Z, self.dH, self.kstar, self.s, self.r, self.beta, self.T, self.dZ)
+        mark("bwd_edges")
+        return self.dZ
+
+    def run(self, Z):
+        self.forward(Z)
+        self.loss_and_grad_logit()
+        return self.backward(Z)

@@ -62,6 +62,14 @@ int dl_csr_build(const int64_t* src, const int64_t* dst, int64_t E, int64_t N, i
                  int32_t* col, int64_t* nnz_out, int32_t* status_out, void* ws, size_t ws_bytes,
                  dl_stream_t stream);
 
+/* General form used by node-partitioned runs: rows in [0,n_rows), columns in [0,n_cols); when
+ * symmetrize == 0 only (src -> dst) entries are produced (the caller lists both directions of the
+ * edges whose row it owns).  dl_csr_build(N) == dl_csr_build_rect(N, N, 1). */
+int dl_csr_build_rect(const int64_t* src, const int64_t* dst, int64_t E, int64_t n_rows,
+                      int64_t n_cols, int symmetrize, int64_t* rowptr, int32_t* col,
+                      int64_t* nnz_out, int32_t* status_out, void* ws, size_t ws_bytes,
+                      dl_stream_t stream);
+
 /* Same, from an already dense 0/1 (any non-zero counts) [N,N] fp32 adjacency that is used as is
  * (no symmetrisation): the drop-in path of Disentangle.forward(x, adj).  [ref: model.py:62]
  * Two calls: count (col == NULL) fills rowptr; fill (col != NULL) writes the columns. */
@@ -89,15 +97,20 @@ int dl_hub_items(const int64_t* rowptr, const int32_t* perm, int64_t n_hub, int6
 
 /* Everything a kernel needs to walk the graph.  Plain-old-data, passed by pointer (host memory). */
 typedef struct dl_graph {
-  int64_t N;
+  int64_t N;                   /* rows held here (all nodes on one GPU; the owned range when the
+                                  nodes are partitioned across GPUs) */
   int64_t nnz;
   const int64_t* rowptr;       /* [N+1] */
-  const int32_t* col;          /* [nnz] */
-  const int32_t* perm;         /* [N] degree-class order, hub rows first */
+  const int32_t* col;          /* [nnz] GLOBAL node ids */
+  const int32_t* perm;         /* [N] local row ids in degree-class order, hub rows first */
   int64_t n_hub;               /* rows with degree >= DL_SEG */
   int64_t n_hub_items;         /* total segments of hub rows */
   const int64_t* hub_seg_ptr;  /* [n_hub+1] */
   const int32_t* item_hub;     /* [n_hub_items] */
+  int64_t row_base;            /* global node id of local row 0: per-node arrays (Z, H, s, r, G,
+                                  dZ) are indexed by row_base + row, i.e. they are full-size
+                                  [N_global, ...] arrays of which this call reads every gathered
+                                  row and writes only the owned slice */
 } dl_graph;
 
 /* ------------------------------------------------------------------------------------------
@@ -125,6 +138,16 @@ int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* ks
 int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const uint8_t* kstar,
                   const float* w, const float* s, int K, int d, float beta, float one_minus_beta,
                   float T, float* dZ, float* r, float* hub_ws, dl_stream_t stream);
+/* The two passes of dl_factor_bwd on their own (a node-partitioned run all-gathers r between
+ * them): pass 1 writes r and adds beta*G + T_ to dZ; pass 2 adds the attention-weight terms. */
+int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
+                         const uint8_t* kstar, const float* w, const float* s, int K, int d,
+                         float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
+                         dl_stream_t stream);
+int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
+                        const uint8_t* kstar, const float* s, const float* r, int K, int d,
+                        float one_minus_beta, float T, float* dZ, float* hub_ws,
+                        dl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (5) factor-weighted link-pair scoring over explicit (u,v) batches.
@@ -143,6 +166,12 @@ size_t dl_pair_incidence_workspace_bytes(int64_t P, int64_t N);
 int dl_pair_incidence(const int32_t* u, const int32_t* v, int64_t P, int64_t N, int64_t* inc_ptr,
                       int32_t* inc_other, int32_t* inc_pair, void* ws, size_t ws_bytes,
                       dl_stream_t stream);
+
+/* Incidence lists of the nodes in [row_lo, row_hi) only (a rank's owned range); inc_ptr has
+ * row_hi-row_lo+1 entries and inc_ptr[last] is the number of incidences kept. */
+int dl_pair_incidence_range(const int32_t* u, const int32_t* v, int64_t P, int64_t row_lo,
+                            int64_t row_hi, int64_t* inc_ptr, int32_t* inc_other, int32_t* inc_pair,
+                            void* ws, size_t ws_bytes, dl_stream_t stream);
 
 /* Backward of the decoder given dS = dL/dlogit [P].  `inc_host` is the incidence structure seen
  * as a graph (rowptr = inc_ptr, col = inc_other, plus perm / hub items from dl_degree_buckets and
