@@ -31,7 +31,7 @@ class DlGraph(_c.Structure):
     """Mirror of ``struct dl_graph``."""
     _fields_ = [("N", _i64), ("nnz", _i64), ("rowptr", _vp), ("col", _vp), ("perm", _vp),
                 ("n_hub", _i64), ("n_hub_items", _i64), ("hub_seg_ptr", _vp), ("item_hub", _vp),
-                ("row_base", _i64)]
+                ("erow", _vp), ("row_base", _i64)]
 
 
 _GP = _c.POINTER(DlGraph)
@@ -44,6 +44,7 @@ SIGNATURES = {
     "dl_csr_build": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dl_csr_build_rect": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dl_csr_from_dense": (_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "dl_entry_rows": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "dl_rev_index": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "dl_degree_buckets_workspace_bytes": (_sz, [_i64]),
     "dl_degree_buckets": (_int, [_vp, _i64, _vp, _vp, _vp, _sz, _vp]),

@@ -17,8 +17,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libdisenlink_b200.so")
-SOURCES = ["graph_build.cu", "factor_fwd.cu", "factor_bwd.cu", "pair_score.cu", "dense_compat.cu"]
-HEADERS = [os.path.join(CSRC, h) for h in ("dl_common.cuh", "dl_dispatch.cuh")] + [
+SOURCES = ["graph_build.cu", "factor_fwd.cu", "attn_stream.cu", "slice_gather.cu", "factor_bwd.cu",
+           "pair_score.cu", "dense_compat.cu"]
+HEADERS = [os.path.join(CSRC, h) for h in ("dl_common.cuh", "dl_dispatch.cuh", "dl_stream.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "disenlink_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=false", "-Xptxas", "-v", "-Wno-deprecated-declarations"]
@@ -63,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     if force or _stale(LIB, objs):
-        cmd = [nvcc] + ccbin + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [nvcc] + ccbin + ["-shared", "-o", LIB] + objs + ["-lcudart", "-Xlinker", "-z", "-Xlinker", "defs"]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

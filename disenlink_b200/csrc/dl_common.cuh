@@ -23,6 +23,10 @@
 #define DL_FULL 0xffffffffu
 #define DL_WARPS_PER_CTA 8
 #define DL_CTA (DL_WARPS_PER_CTA * 32)
+// the register-heavy, double-buffered row-gather kernels use small CTAs so the register file is
+// filled at a finer granularity
+#define DL_WARPS_PER_CTA_S 4
+#define DL_CTA_S (DL_WARPS_PER_CTA_S * 32)
 
 #define DL_CUDA_TRY(expr)                    \
   do {                                       \
@@ -45,6 +49,7 @@ struct DlGraphDev {
   long long n_hub, n_hub_items;
   const long long* __restrict__ hub_seg_ptr;
   const int* __restrict__ item_hub;
+  const int* __restrict__ erow;
   long long row_base;
 };
 
@@ -56,6 +61,7 @@ static inline DlGraphDev dl_graph_dev(const dl_graph* g) {
   o.n_hub = g->n_hub; o.n_hub_items = g->n_hub_items;
   o.hub_seg_ptr = (const long long*)g->hub_seg_ptr;
   o.item_hub = g->item_hub;
+  o.erow = g->erow;
   o.row_base = g->row_base;
   return o;
 }
@@ -102,6 +108,36 @@ __device__ __forceinline__ DlItem dl_decode_item(const DlGraphDev& g, long long 
   it.node = g.row_base + it.row;
   return it;
 }
+
+// Software-pipelined work-item iterator.  Hub segments come first (they are long, the decode cost is
+// amortised), then the regular rows in NATURAL order with a warp stride, skipping hub rows.  The row
+// bounds of the next two rows of this warp are always in flight, so the rowptr -> col -> gather
+// dependency chain of one row overlaps the gathers of the previous one.
+struct DlRowIter {
+  long long W, t, r, a0, a1, b0, b1;
+  __device__ __forceinline__ void init(const DlGraphDev& g, long long warp0, long long nwarps) {
+    W = nwarps; t = warp0; r = warp0;
+    a0 = a1 = b0 = b1 = 0;
+    if (r < g.N) { a0 = __ldg(g.rowptr + r); a1 = __ldg(g.rowptr + r + 1); }
+    if (r + W < g.N) { b0 = __ldg(g.rowptr + r + W); b1 = __ldg(g.rowptr + r + W + 1); }
+  }
+  __device__ __forceinline__ bool next(const DlGraphDev& g, DlItem& it) {
+    if (t < g.n_hub_items) {
+      it = dl_decode_item(g, t);
+      t += W;
+      return true;
+    }
+    while (r < g.N) {
+      const long long cr = r, c0 = a0, c1 = a1;
+      r += W; a0 = b0; a1 = b1;
+      if (r + W < g.N) { b0 = __ldg(g.rowptr + r + W); b1 = __ldg(g.rowptr + r + W + 1); }
+      if (c1 - c0 >= (long long)DL_SEG) continue;   // hub row: handled as segments above
+      it.row = (int)cr; it.node = g.row_base + cr; it.e0 = c0; it.e1 = c1; it.hub_slot = -1;
+      return true;
+    }
+    return false;
+  }
+};
 
 // ---- canonical exp ------------------------------------------------------------------------
 __device__ __forceinline__ float dl_expf(float x) {
@@ -251,13 +287,15 @@ __device__ __forceinline__ float dl_group_sum(float v) {
 // Persistent-style grid: (#SMs) x (resident CTAs per SM) CTAs of DL_CTA threads, warps stride
 // over the work items.
 template <class Kernel>
-static inline int dl_grid_for(Kernel kern, long long n_items, int* grid_out) {
+static inline int dl_grid_for(Kernel kern, long long n_items, int* grid_out, size_t smem_bytes = 0,
+                              int cta_threads = DL_CTA) {
   int dev = 0, sms = 0, per_sm = 0;
   DL_CUDA_TRY(cudaGetDevice(&dev));
   DL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  DL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DL_CTA, 0));
+  DL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, cta_threads, smem_bytes));
   if (per_sm < 1) per_sm = 1;
-  long long want = (n_items + DL_WARPS_PER_CTA - 1) / DL_WARPS_PER_CTA;
+  const int wpc = cta_threads / 32;
+  long long want = (n_items + wpc - 1) / wpc;
   long long cap = (long long)sms * per_sm;
   long long grid = want < cap ? want : cap;
   if (grid < 1) grid = 1;

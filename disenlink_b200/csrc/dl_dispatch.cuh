@@ -85,3 +85,16 @@ __device__ __forceinline__ int dl_generic_route(const float* __restrict__ zi,
   }
   return best;
 }
+
+// Shared launcher of the slice-gather kernel (slice_gather.cu).  mode 0: aggregation forward
+// (SRC = Z, OUT = H); mode 1: backward pass 1 (SRC = G, OUT = dZ accumulated, r written, hub rows
+// finished by their own kernel).  Returns -1000 when (K, d) has no fast-path instantiation.
+int dl_launch_slice_gather(int mode, const DlGraphDev& g, long long n_items, const float* Z,
+                           const float* SRC, const unsigned char* kstar, const float* w,
+                           const float* s, int K, int d, float beta, float omb, float* OUT, float* r,
+                           float* hub_ws, cudaStream_t st);
+
+// Streaming attention (attn_stream.cu): routing + row sums.  Returns -1000 when (K, d) has no
+// streaming instantiation.
+int dl_launch_attn_stream(const DlGraphDev& g, const int* erow, const float* Z, int K, int d, float T,
+                          unsigned char* kstar, float* w, float* s, float* hub_ws, cudaStream_t st);

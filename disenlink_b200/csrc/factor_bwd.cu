@@ -19,130 +19,13 @@
 
 namespace {
 
-// epilogue of pass 1 for one row held in fast-path lane layout
-template <class M>
-__device__ __forceinline__ void bwd_gather_epilogue(int lane, long long row, const float4 (&acc)[M::NP],
-                                                    const float* __restrict__ Z, const float* __restrict__ G,
-                                                    const float* __restrict__ s, float beta, float omb,
-                                                    float* __restrict__ dZ, float* __restrict__ r) {
-  constexpr int K = M::K, D = M::D, NP = M::NP, LP = M::LP;
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    const int k = M::factor(lane, p);
-    const bool act = M::active(lane, p);
-    const int o = M::offset(lane, p);
-    const float sk = (k < K) ? __ldg(s + row * K + k) : 1.0f;
-    const float scale = __fdiv_rn(omb, sk);
-    float4 tv;
-    tv.x = __fmul_rn(scale, acc[p].x); tv.y = __fmul_rn(scale, acc[p].y);
-    tv.z = __fmul_rn(scale, acc[p].z); tv.w = __fmul_rn(scale, acc[p].w);
-    const float4 zi = act ? dl_ldg4(Z + row * D + o) : dl_zero4();
-    const float dotzt = dl_group_sum<M>(dl_chunk_dot(zi, tv));
-    if (k < K && (lane % LP) == 0) r[row * K + k] = __fdiv_rn(dotzt, sk);
-    if (act) {
-      const float4 gi = dl_ldg4(G + row * D + o);
-      float4* dst = reinterpret_cast<float4*>(dZ + row * D + o);
-      float4 cur = *dst;
-      cur.x = __fadd_rn(cur.x, __fmaf_rn(beta, gi.x, tv.x));
-      cur.y = __fadd_rn(cur.y, __fmaf_rn(beta, gi.y, tv.y));
-      cur.z = __fadd_rn(cur.z, __fmaf_rn(beta, gi.z, tv.z));
-      cur.w = __fadd_rn(cur.w, __fmaf_rn(beta, gi.w, tv.w));
-      *dst = cur;
-    }
-  }
-}
+struct EMeta {
+  int c, kk;
+  float sj, rj;
+};
 
 template <class M>
-__global__ void __launch_bounds__(DL_CTA)
-k_factor_bwd_gather(DlGraphDev g, const float* __restrict__ Z, const float* __restrict__ G,
-                    const unsigned char* __restrict__ kstar, const float* __restrict__ w,
-                    const float* __restrict__ s, float beta, float omb, float* __restrict__ dZ,
-                    float* __restrict__ r, float* __restrict__ hub_ws) {
-  constexpr int K = M::K, d = M::d, D = M::D, NP = M::NP, L = M::L, FPP = M::FPP;
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * DL_WARPS_PER_CTA + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * DL_WARPS_PER_CTA;
-  const long long n_items = dl_num_items(g);
-  const int slot = M::slot(lane), gg = M::g(lane);
-  const bool glane = gg < L;
-
-  for (long long t = warp0; t < n_items; t += nwarps) {
-    const DlItem it = dl_decode_item(g, t);
-    float4 acc[NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) acc[p] = dl_zero4();
-    for (long long base = it.e0; base < it.e1; base += 32) {
-      const int cnt = (int)min(32LL, it.e1 - base);
-      int c = 0, k = 255;
-      float wv = 0.0f;
-      if (lane < cnt) {
-        c = __ldg(g.col + base + lane);
-        k = __ldg(kstar + base + lane);
-        wv = __ldg(w + base + lane);
-      }
-      for (int i0 = 0; i0 < cnt; i0 += 8) {
-        float4 z[8];
-        float cf[8];
-        int pk[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int idx = i0 + u;
-          const int cc = __shfl_sync(DL_FULL, c, idx);
-          const int kk = __shfl_sync(DL_FULL, k, idx);
-          cf[u] = __shfl_sync(DL_FULL, wv, idx);
-          const bool m = glane && (kk % FPP) == slot && kk < K;
-          pk[u] = m ? kk / FPP : -1;
-          z[u] = m ? dl_ldg4(G + (long long)cc * D + kk * d + 4 * gg) : dl_zero4();
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-#pragma unroll
-          for (int p = 0; p < NP; ++p)
-            if (pk[u] == p) dl_fma4(acc[p], cf[u], z[u]);
-        }
-      }
-    }
-    if (it.hub_slot >= 0) {
-#pragma unroll
-      for (int p = 0; p < NP; ++p)
-        if (M::active(lane, p))
-          *reinterpret_cast<float4*>(hub_ws + it.hub_slot * D + M::offset(lane, p)) = acc[p];
-    } else {
-      bwd_gather_epilogue<M>(lane, it.node, acc, Z, G, s, beta, omb, dZ, r);
-    }
-  }
-}
-
-// hub rows of pass 1: one warp per hub row sums the segment partials (in order), then the epilogue
-template <class M>
-__global__ void __launch_bounds__(DL_CTA)
-k_factor_bwd_gather_hub(DlGraphDev g, const float* __restrict__ Z, const float* __restrict__ G,
-                        const float* __restrict__ s, float beta, float omb, float* __restrict__ dZ,
-                        float* __restrict__ r, const float* __restrict__ hub_ws) {
-  constexpr int D = M::D, NP = M::NP;
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * DL_WARPS_PER_CTA + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * DL_WARPS_PER_CTA;
-  for (long long h = warp0; h < g.n_hub; h += nwarps) {
-    const long long a = g.hub_seg_ptr[h], b = g.hub_seg_ptr[h + 1];
-    float4 acc[NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) acc[p] = dl_zero4();
-    for (long long sg = a; sg < b; ++sg) {
-#pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        if (!M::active(lane, p)) continue;
-        const float4 v = *reinterpret_cast<const float4*>(hub_ws + sg * D + M::offset(lane, p));
-        acc[p].x = __fadd_rn(acc[p].x, v.x); acc[p].y = __fadd_rn(acc[p].y, v.y);
-        acc[p].z = __fadd_rn(acc[p].z, v.z); acc[p].w = __fadd_rn(acc[p].w, v.w);
-      }
-    }
-    bwd_gather_epilogue<M>(lane, g.row_base + g.perm[h], acc, Z, G, s, beta, omb, dZ, r);
-  }
-}
-
-template <class M>
-__global__ void __launch_bounds__(DL_CTA)
+__global__ void __launch_bounds__(DL_CTA, (M::NP == 1 ? 2 : 1))
 k_factor_bwd_edges(DlGraphDev g, const float* __restrict__ Z, const float* __restrict__ G,
                    const unsigned char* __restrict__ kstar, const float* __restrict__ s,
                    const float* __restrict__ r, float omb, float T, float* __restrict__ dZ,
@@ -151,32 +34,69 @@ k_factor_bwd_edges(DlGraphDev g, const float* __restrict__ Z, const float* __res
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * DL_WARPS_PER_CTA + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * DL_WARPS_PER_CTA;
-  const long long n_items = dl_num_items(g);
   const int my_e = M::edge_of_lane(lane);
   const int gsrc = lane & (EB - 1);
   const int gbase = lane & ~(LP - 1);
   const int slot = M::slot(lane), gg = M::g(lane);
   const bool glane = gg < L;
+  const bool unit_T = (T == 1.0f);
 
-  for (long long t = warp0; t < n_items; t += nwarps) {
-    const DlItem it = dl_decode_item(g, t);
-    float4 zi[NP], gi[NP], dz[NP];
+  auto load_ck = [&](const DlItem& it, EMeta& m) {
+    m.c = 0; m.kk = 255; m.sj = 1.0f; m.rj = 0.0f;
+    if (lane < it.e1 - it.e0) {
+      m.c = __ldg(g.col + it.e0 + lane);
+      m.kk = __ldg(kstar + it.e0 + lane);
+    }
+  };
+  auto load_sr = [&](EMeta& m) {
+    if (m.kk != 255) {
+      m.sj = __ldg(s + (long long)m.c * K + m.kk);
+      m.rj = __ldg(r + (long long)m.c * K + m.kk);
+    }
+  };
+  auto load_row = [&](const DlItem& it, float4 (&zi)[NP], float4 (&gi)[NP]) {
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       const bool act = M::active(lane, p);
       zi[p] = act ? dl_ldg4(Z + it.node * D + M::offset(lane, p)) : dl_zero4();
       gi[p] = act ? dl_ldg4(G + it.node * D + M::offset(lane, p)) : dl_zero4();
-      dz[p] = dl_zero4();
     }
-    for (long long base = it.e0; base < it.e1; base += 32) {
-      const int cnt = (int)min(32LL, it.e1 - base);
-      int c = 0, kk = 255;
-      float sj = 1.0f, rj = 0.0f;
-      if (lane < cnt) {
-        c = __ldg(g.col + base + lane);
-        kk = __ldg(kstar + base + lane);
-        sj = __ldg(s + (long long)c * K + kk);
-        rj = __ldg(r + (long long)c * K + kk);
+  };
+
+  DlRowIter itr;
+  itr.init(g, warp0, nwarps);
+  DlItem it0, it1, it2;
+  EMeta m0, m1, m2;
+  it0 = it1 = it2 = DlItem{0, 0, 0, 0, -1};
+  m0 = m1 = m2 = EMeta{0, 255, 1.0f, 0.0f};
+  float4 zi[NP], gi[NP], ziB[NP], giB[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) zi[p] = gi[p] = ziB[p] = giB[p] = dl_zero4();
+  bool h0 = itr.next(g, it0), h1 = false, h2 = false;
+  if (h0) { load_ck(it0, m0); load_sr(m0); load_row(it0, zi, gi); }
+  h1 = h0 && itr.next(g, it1);
+  if (h1) load_ck(it1, m1);
+
+  while (h0) {
+    if (h1) { load_sr(m1); load_row(it1, ziB, giB); }   // in flight during this item
+    h2 = h1 && itr.next(g, it2);
+    if (h2) load_ck(it2, m2);
+
+    float4 dz[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) dz[p] = dl_zero4();
+    for (long long base = it0.e0; base < it0.e1; base += 32) {
+      const int cnt = (int)min(32LL, it0.e1 - base);
+      int c = m0.c, kk = m0.kk;
+      float sj = m0.sj, rj = m0.rj;
+      if (base != it0.e0) {
+        c = 0; kk = 255; sj = 1.0f; rj = 0.0f;
+        if (lane < cnt) {
+          c = __ldg(g.col + base + lane);
+          kk = __ldg(kstar + base + lane);
+          sj = __ldg(s + (long long)c * K + kk);
+          rj = __ldg(r + (long long)c * K + kk);
+        }
       }
       const int nsub = (cnt + EB - 1) / EB;
       for (int sb = 0; sb < nsub; ++sb) {
@@ -186,7 +106,7 @@ k_factor_bwd_edges(DlGraphDev g, const float* __restrict__ Z, const float* __res
         for (int e = 0; e < EB; ++e) {
           const int idx = sb * EB + e;
           const int cc = __shfl_sync(DL_FULL, c, idx & 31);
-          const int ke = __shfl_sync(DL_FULL, kk, idx & 31);
+          const int ke = __shfl_sync(DL_FULL, kk, idx & 31);   // 255 beyond cnt
           const bool valid = idx < cnt;
 #pragma unroll
           for (int p = 0; p < NP; ++p)
@@ -196,30 +116,29 @@ k_factor_bwd_edges(DlGraphDev g, const float* __restrict__ Z, const float* __res
           gpass[e] = m ? ke / FPP : -1;
           gje[e] = m ? dl_ldg4(G + (long long)cc * D + ke * d + 4 * gg) : dl_zero4();
         }
-        // routing recomputed in canonical arithmetic (bit-identical to the forward)
+        // softmax over the factors recomputed in canonical arithmetic (bit-identical to forward)
         float ev[NP];
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
           float part[EB];
 #pragma unroll
           for (int e = 0; e < EB; ++e) part[e] = dl_chunk_dot(zi[p], zj[e][p]);
-          ev[p] = dl_expf(__fdiv_rn(dl_reduce_scatter<M>(part, lane), T));
+          float q = dl_reduce_scatter<M>(part, lane);
+          if (!unit_T) q = __fdiv_rn(q, T);
+          ev[p] = dl_expf(q);
         }
-        float sum = 0.0f;
-        float a[K];
+        const int my_idx = sb * EB + my_e;
+        const bool valid = my_idx < cnt;
+        int ks = __shfl_sync(DL_FULL, kk, my_idx & 31);        // stored routing of my edge
+        ks = valid ? ks : 0;
+        float sum = 0.0f, eks = 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          a[k] = __shfl_sync(DL_FULL, ev[k / FPP], (k % FPP) * LP + gsrc);
-          sum = (k == 0) ? a[0] : __fadd_rn(sum, a[k]);
+          const float ek = __shfl_sync(DL_FULL, ev[k / FPP], (k % FPP) * LP + gsrc);
+          sum = (k == 0) ? ek : __fadd_rn(sum, ek);
+          if (k == ks) eks = ek;
         }
-        int ks = 0;
-        float wv = 0.0f;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          float v = __fdiv_rn(a[k], sum);
-          if (k == 0) { wv = v; }
-          else if (v > wv || (v != v && wv == wv)) { wv = v; ks = k; }
-        }
+        const float wv = __fdiv_rn(eks, sum);                  // = w[e] of the forward, same bits
         // c_ij = (1-beta) <G[i,ks], Z[j,ks]>, c_ji = (1-beta) <G[j,ks], Z[i,ks]>: partials exist only
         // on the lanes that own factor kstar(e) of edge e
         float pij[EB], pji[EB];
@@ -241,16 +160,16 @@ k_factor_bwd_edges(DlGraphDev g, const float* __restrict__ Z, const float* __res
         const int ksrc = (ks % FPP) * LP + gsrc;
         const float cij = __fmul_rn(omb, __shfl_sync(DL_FULL, rij, ksrc));
         const float cji = __fmul_rn(omb, __shfl_sync(DL_FULL, rji, ksrc));
-        const int my_idx = sb * EB + my_e;
-        const bool valid = my_idx < cnt;
         const float sjv = __shfl_sync(DL_FULL, sj, my_idx & 31);
         const float rjv = __shfl_sync(DL_FULL, rj, my_idx & 31);
-        const float siv = __ldg(s + it.node * K + ks);
-        const float riv = __ldg(r + it.node * K + ks);
+        const float siv = __ldg(s + it0.node * K + ks);
+        const float riv = __ldg(r + it0.node * K + ks);
         float dws = __fadd_rn(__fdiv_rn(cij, sjv), __fdiv_rn(cji, siv));
         dws = __fsub_rn(dws, riv);
         dws = __fsub_rn(dws, rjv);
-        const float basec = valid ? __fdiv_rn(__fmul_rn(dws, wv), T) : 0.0f;
+        float basec = __fmul_rn(dws, wv);
+        if (!unit_T) basec = __fdiv_rn(basec, T);
+        basec = valid ? basec : 0.0f;
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
           const float a_own = __fdiv_rn(ev[p], sum);
@@ -268,16 +187,20 @@ k_factor_bwd_edges(DlGraphDev g, const float* __restrict__ Z, const float* __res
     for (int p = 0; p < NP; ++p) {
       if (!M::active(lane, p)) continue;
       const int o = M::offset(lane, p);
-      if (it.hub_slot >= 0) {
-        *reinterpret_cast<float4*>(hub_ws + it.hub_slot * D + o) = dz[p];
+      if (it0.hub_slot >= 0) {
+        *reinterpret_cast<float4*>(hub_ws + it0.hub_slot * D + o) = dz[p];
       } else {
-        float4* dst = reinterpret_cast<float4*>(dZ + it.node * D + o);
+        float4* dst = reinterpret_cast<float4*>(dZ + it0.node * D + o);
         float4 cur = *dst;
         cur.x = __fadd_rn(cur.x, dz[p].x); cur.y = __fadd_rn(cur.y, dz[p].y);
         cur.z = __fadd_rn(cur.z, dz[p].z); cur.w = __fadd_rn(cur.w, dz[p].w);
         *dst = cur;
       }
     }
+    it0 = it1; m0 = m1; h0 = h1;
+    it1 = it2; m1 = m2; h1 = h2;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { zi[p] = ziB[p]; gi[p] = giB[p]; }
   }
 }
 
@@ -445,24 +368,6 @@ inline int fixup_blocks(long long n) {
 }
 
 template <class M>
-int launch_bwd_gather(const DlGraphDev& g, long long n_items, const float* Z, const float* G,
-                      const uint8_t* kstar, const float* w, const float* s, float beta, float omb,
-                      float* dZ, float* r, float* hub_ws, cudaStream_t st) {
-  int grid = 1;
-  int rc = dl_grid_for(k_factor_bwd_gather<M>, n_items, &grid);
-  if (rc) return rc;
-  k_factor_bwd_gather<M><<<grid, DL_CTA, 0, st>>>(g, Z, G, kstar, w, s, beta, omb, dZ, r, hub_ws);
-  DL_LAUNCH_CHECK();
-  if (g.n_hub > 0) {
-    rc = dl_grid_for(k_factor_bwd_gather_hub<M>, g.n_hub, &grid);
-    if (rc) return rc;
-    k_factor_bwd_gather_hub<M><<<grid, DL_CTA, 0, st>>>(g, Z, G, s, beta, omb, dZ, r, hub_ws);
-    DL_LAUNCH_CHECK();
-  }
-  return DL_OK;
-}
-
-template <class M>
 int launch_bwd_edges(const DlGraphDev& g, long long n_items, const float* Z, const float* G,
                      const uint8_t* kstar, const float* s, const float* r, float omb, float T,
                      float* dZ, float* hub_ws, cudaStream_t st) {
@@ -489,11 +394,8 @@ int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
   cudaStream_t st = (cudaStream_t)stream;
   const DlGraphDev g = dl_graph_dev(g_host);
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
-  int rc = -1000;
-#define BODY_MACRO(M) \
-  rc = launch_bwd_gather<M>(g, n_items, Z, G, kstar, w, s, beta, one_minus_beta, dZ, r, hub_ws, st);
-  DL_DISPATCH_SHAPES()
-#undef BODY_MACRO
+  int rc = dl_launch_slice_gather(1, g, n_items, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r,
+                                  hub_ws, st);
   if (rc == -1000) {
     int grid = 1;
     rc = dl_grid_for(k_factor_bwd_gather_generic, n_items, &grid);

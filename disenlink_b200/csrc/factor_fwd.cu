@@ -4,17 +4,30 @@
 //                     the K factors, hard routing kstar = first argmax, w = a[kstar]; per row the
 //                     routed sums s[i,k] (zeros -> 1).  Everything stays in registers; only
 //                     (kstar: u8, w: f32) per entry and s [N,K] are written.
-//   k_factor_spmm_fwd [ref: model.py:75]     H[i,k] = beta Z[i,k] + (1-beta) sum_{j: kstar=k}
-//                     (w_ij / s[j,k]) Z[j,k]  -- gather / segment-sum in column order, no atomics.
+//   k_factor_gather   [ref: model.py:75]     H[i,k] = beta Z[i,k] + (1-beta) sum_{j: kstar=k}
+//                     (w_ij / s[j,k]) Z[j,k]  -- gather / segment-sum, no atomics.  The same kernel
+//                     (MODE 1) is pass 1 of the backward: T_[i,k] = (1-beta)/s[i,k] sum w G[j,k].
 //
-// Mapping (fast path, DlMap<K,d>): one warp per work item (a row, or a DL_SEG-edge segment of a
-// hub row).  A row of D = K*d floats is spread over the lanes as float4 chunks, so a neighbour
-// row is one coalesced 128-bit-per-lane gather.  Four edges are in flight per warp step; their
-// chunk partials are reduce-scattered over the d/4-lane factor group (3 shuffles per 4 edges
-// instead of 8), giving lane (k, g) the finished dot of edge g for factor k.
+// Work distribution: one warp per work item (a row, or a DL_SEG-edge segment of a hub row), rows in
+// natural order with a warp stride, software-pipelined (DlRowIter + per-kernel prefetch of the next
+// item's first column block / row vectors) so the rowptr -> col -> gather dependency chain of one
+// row overlaps the gathers of the previous row.
+//
+// Attention mapping (DlMap<K,d>): a row of D = K*d floats is spread over the lanes as float4
+// chunks, so a neighbour row is one coalesced 128-bit-per-lane gather.  Four edges are in flight
+// per warp step; their chunk partials are reduce-scattered over the d/4-lane factor group
+// (3 shuffles per 4 edges instead of 8), giving lane (k, g) the finished dot of edge g, factor k.
+//
+// Slice-gather mapping: only the kstar slice (d floats) of a neighbour is needed, so the warp is
+// split into NG = 32/LP lane groups that fetch NG different edges per load instruction (8 x 64 B
+// at d = 16); each lane keeps K float4 accumulators (predicated on the edge's factor), and the NG
+// group partials are combined in a fixed order through shared memory at the end of the row.
 //
 // HBM bytes per entry (D=128, K=8, d=16): attention 4 (col) + 512 (z_j) + 5 (kstar, w);
 // aggregation 4 + 5 + 4 (s[j,k]) + 64 (z_j^k slice).  Per row: z_i, s / H.  DESIGN.md section 4.
+#include <math_constants.h>
+#include <stdlib.h>
+
 #include "dl_dispatch.cuh"
 
 namespace {
@@ -23,14 +36,13 @@ namespace {
 // attention, fast path
 // ---------------------------------------------------------------------------------------------
 template <class M>
-__global__ void __launch_bounds__(DL_CTA)
+__global__ void __launch_bounds__(DL_CTA_S)
 k_edge_attn_fwd(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __restrict__ kstar,
                 float* __restrict__ w, float* __restrict__ s, float* __restrict__ hub_ws) {
   constexpr int K = M::K, D = M::D, NP = M::NP, EB = M::EB, LP = M::LP, FPP = M::FPP;
   const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * DL_WARPS_PER_CTA + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * DL_WARPS_PER_CTA;
-  const long long n_items = dl_num_items(g);
+  const long long warp0 = (long long)blockIdx.x * DL_WARPS_PER_CTA_S + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * DL_WARPS_PER_CTA_S;
 
   int off[NP];
   bool act[NP];
@@ -39,43 +51,77 @@ k_edge_attn_fwd(DlGraphDev g, const float* __restrict__ Z, float T, unsigned cha
   const int my_e = M::edge_of_lane(lane);
   const int gsrc = lane & (EB - 1);
   const bool primary = (lane % LP) < EB;  // one replica per (factor, edge) accumulates s
+  const bool unit_T = (T == 1.0f);
 
-  for (long long t = warp0; t < n_items; t += nwarps) {
-    const DlItem it = dl_decode_item(g, t);
+  // gather the EB neighbour rows of one sub-block: columns idx0.. of the 32-column block held in
+  // `colreg` (one column per lane), valid while idx < lim
+  auto fetch = [&](float4 (&dst)[EB][NP], int colreg, int idx0, int lim) {
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      const int idx = idx0 + e;
+      const int c = __shfl_sync(DL_FULL, colreg, idx & 31);
+      const bool valid = idx < lim;
+#pragma unroll
+      for (int p = 0; p < NP; ++p)
+        dst[e][p] = (valid && act[p]) ? dl_ldg4(Z + (long long)c * D + off[p]) : dl_zero4();
+    }
+  };
+
+  DlRowIter itr;
+  itr.init(g, warp0, nwarps);
+  DlItem it, nit;
+  it = nit = DlItem{0, 0, 0, 0, -1};
+  bool have = itr.next(g, it);
+  int colA = 0;
+  if (have && lane < it.e1 - it.e0) colA = __ldg(g.col + it.e0 + lane);
+  // zjA always holds the rows of the sub-block about to be computed; while it is being computed
+  // the rows of the NEXT sub-block in stream order (same block / next block of the row / first
+  // block of the next item) are in flight into zjB.
+  float4 zjA[EB][NP], zjB[EB][NP];
+  bool pre = false;   // zjA already holds the first sub-block of `it`
+
+  while (have) {
+    const bool have_n = itr.next(g, nit);
+    const int ncntB = have_n ? (int)min(32LL, nit.e1 - nit.e0) : 0;
+    int colB = 0;
+    if (lane < ncntB) colB = __ldg(g.col + nit.e0 + lane);
     float4 zi[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) zi[p] = act[p] ? dl_ldg4(Z + it.node * D + off[p]) : dl_zero4();
+    if (!pre && it.e1 > it.e0) fetch(zjA, colA, 0, (int)min(32LL, it.e1 - it.e0));
+    bool pre_n = false;
+
     float sacc[NP];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      zi[p] = act[p] ? dl_ldg4(Z + it.node * D + off[p]) : dl_zero4();
-      sacc[p] = 0.0f;
-    }
+    for (int p = 0; p < NP; ++p) sacc[p] = 0.0f;
+    int mycol = colA, colN = 0;
     for (long long base = it.e0; base < it.e1; base += 32) {
       const int cnt = (int)min(32LL, it.e1 - base);
-      const int mycol = lane < cnt ? __ldg(g.col + base + lane) : 0;
+      const bool more = base + 32 < it.e1;
+      const int ncntN = more ? (int)min(32LL, it.e1 - base - 32) : 0;
+      if (lane < ncntN) colN = __ldg(g.col + base + 32 + lane);
       int out_ks = 0;
       float out_w = 0.0f;
       const int nsub = (cnt + EB - 1) / EB;
       for (int sb = 0; sb < nsub; ++sb) {
-        float4 zj[EB][NP];
-#pragma unroll
-        for (int e = 0; e < EB; ++e) {
-          const int idx = sb * EB + e;
-          const int c = __shfl_sync(DL_FULL, mycol, idx & 31);
-          const bool valid = idx < cnt;
-#pragma unroll
-          for (int p = 0; p < NP; ++p)
-            zj[e][p] = (valid && act[p]) ? dl_ldg4(Z + (long long)c * D + off[p]) : dl_zero4();
+        {   // prefetch the next sub-block in stream order
+          int pc, pi0, plim;
+          if (sb + 1 < nsub) { pc = mycol; pi0 = (sb + 1) * EB; plim = cnt; }
+          else if (more) { pc = colN; pi0 = 0; plim = ncntN; }
+          else { pc = colB; pi0 = 0; plim = ncntB; pre_n = ncntB > 0; }
+          fetch(zjB, pc, pi0, plim);
         }
         float ev[NP];
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
           float part[EB];
 #pragma unroll
-          for (int e = 0; e < EB; ++e) part[e] = dl_chunk_dot(zi[p], zj[e][p]);
-          float q = __fdiv_rn(dl_reduce_scatter<M>(part, lane), T);
+          for (int e = 0; e < EB; ++e) part[e] = dl_chunk_dot(zi[p], zjA[e][p]);
+          float q = dl_reduce_scatter<M>(part, lane);
+          if (!unit_T) q = __fdiv_rn(q, T);
           ev[p] = dl_expf(q);
         }
-        // all-gather the K exponentials of my edge, then the softmax / argmax in registers
+        // all-gather the K exponentials of my edge
         float a[K];
         float sum = 0.0f;
 #pragma unroll
@@ -83,25 +129,49 @@ k_edge_attn_fwd(DlGraphDev g, const float* __restrict__ Z, float T, unsigned cha
           a[k] = __shfl_sync(DL_FULL, ev[k / FPP], (k % FPP) * LP + gsrc);
           sum = (k == 0) ? a[0] : __fadd_rn(sum, a[k]);
         }
+        // routing = first argmax of a_k = e_k / sum.  Division is monotone, so when the largest
+        // exponential is separated from every other one by more than 2^-22 relative (>= 2 float
+        // spacings) its quotient is strictly the largest and one division suffices; exact ties in e
+        // resolve to the first index either way.  Anything closer (or non-finite) takes the
+        // literal path.  Both paths return the same bits.
         int ks = 0;
-        float wv = 0.0f;
+        float emax = a[0];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          float v = __fdiv_rn(a[k], sum);
-          if (k == 0) { wv = v; }
-          else if (v > wv || (v != v && wv == wv)) { wv = v; ks = k; }
+        for (int k = 1; k < K; ++k)
+          if (a[k] > emax) { emax = a[k]; ks = k; }
+        const float thr = __fmul_rn(emax, 0.99999976158142089844f);  // 1 - 2^-22
+        bool slow = !(sum < CUDART_INF_F);
+#pragma unroll
+        for (int k = 0; k < K; ++k) slow = slow || (a[k] > thr && a[k] != emax);
+        float wv;
+        if (!slow) {
+          wv = __fdiv_rn(emax, sum);
+        } else {
+          ks = 0;
+          wv = 0.0f;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            float v = __fdiv_rn(a[k], sum);
+            if (k == 0) { wv = v; }
+            else if (v > wv || (v != v && wv == wv)) { wv = v; ks = k; }
+          }
         }
         const bool valid = (sb * EB + my_e) < cnt;
 #pragma unroll
         for (int p = 0; p < NP; ++p)
           if (valid && primary && ks == M::factor(lane, p)) sacc[p] = __fadd_rn(sacc[p], wv);
         if (sb == lane / EB) { out_ks = ks; out_w = wv; }
+#pragma unroll
+        for (int e = 0; e < EB; ++e)
+#pragma unroll
+          for (int p = 0; p < NP; ++p) zjA[e][p] = zjB[e][p];
       }
       const int oi = (lane & ~(EB - 1)) + my_e;
       if (oi < cnt) {
         kstar[base + oi] = (unsigned char)out_ks;
         w[base + oi] = out_w;
       }
+      mycol = colN;
     }
     // per-row routed sums: combine the EB interleaved chains, fixed tree
 #pragma unroll
@@ -115,6 +185,10 @@ k_edge_attn_fwd(DlGraphDev g, const float* __restrict__ Z, float T, unsigned cha
         else s[it.node * K + k] = (v == 0.0f) ? 1.0f : v;
       }
     }
+    it = nit;
+    have = have_n;
+    colA = colB;
+    pre = pre_n;
   }
 }
 
@@ -162,79 +236,6 @@ __global__ void k_attn_hub_fixup(DlGraphDev g, int K, const float* __restrict__ 
     float v = 0.0f;
     for (long long sg = a; sg < b; ++sg) v = __fadd_rn(v, hub_ws[sg * K + k]);
     s[(g.row_base + g.perm[h]) * K + k] = (v == 0.0f) ? 1.0f : v;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// aggregation, fast path
-// ---------------------------------------------------------------------------------------------
-template <class M>
-__global__ void __launch_bounds__(DL_CTA)
-k_factor_spmm_fwd(DlGraphDev g, const float* __restrict__ Z, const unsigned char* __restrict__ kstar,
-                  const float* __restrict__ w, const float* __restrict__ s, float beta, float omb,
-                  float* __restrict__ H, float* __restrict__ hub_ws) {
-  constexpr int K = M::K, d = M::d, D = M::D, NP = M::NP, L = M::L, FPP = M::FPP;
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * DL_WARPS_PER_CTA + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * DL_WARPS_PER_CTA;
-  const long long n_items = dl_num_items(g);
-  const int slot = M::slot(lane), gg = M::g(lane);
-  const bool glane = gg < L;
-
-  for (long long t = warp0; t < n_items; t += nwarps) {
-    const DlItem it = dl_decode_item(g, t);
-    float4 acc[NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) acc[p] = dl_zero4();
-    for (long long base = it.e0; base < it.e1; base += 32) {
-      const int cnt = (int)min(32LL, it.e1 - base);
-      int c = 0, k = 255;
-      float coef = 0.0f;
-      if (lane < cnt) {
-        c = __ldg(g.col + base + lane);
-        k = __ldg(kstar + base + lane);
-        float wv = __ldg(w + base + lane);
-        float sj = __ldg(s + (long long)c * K + k);
-        coef = __fdiv_rn(wv, sj);
-      }
-      for (int i0 = 0; i0 < cnt; i0 += 8) {
-        float4 z[8];
-        float cf[8];
-        int pk[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int idx = i0 + u;  // < 32; lanes >= cnt carry k = 255 and match nothing
-          const int cc = __shfl_sync(DL_FULL, c, idx);
-          const int kk = __shfl_sync(DL_FULL, k, idx);
-          cf[u] = __shfl_sync(DL_FULL, coef, idx);
-          const bool m = glane && (kk % FPP) == slot && kk < K;
-          pk[u] = m ? kk / FPP : -1;
-          z[u] = m ? dl_ldg4(Z + (long long)cc * D + kk * d + 4 * gg) : dl_zero4();
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-#pragma unroll
-          for (int p = 0; p < NP; ++p)
-            if (pk[u] == p) dl_fma4(acc[p], cf[u], z[u]);
-        }
-      }
-    }
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      if (!M::active(lane, p)) continue;
-      const int o = M::offset(lane, p);
-      if (it.hub_slot >= 0) {
-        *reinterpret_cast<float4*>(hub_ws + it.hub_slot * D + o) = acc[p];
-      } else {
-        const float4 zi = dl_ldg4(Z + it.node * D + o);
-        float4 h;
-        h.x = __fadd_rn(__fmul_rn(beta, zi.x), __fmul_rn(omb, acc[p].x));
-        h.y = __fadd_rn(__fmul_rn(beta, zi.y), __fmul_rn(omb, acc[p].y));
-        h.z = __fadd_rn(__fmul_rn(beta, zi.z), __fmul_rn(omb, acc[p].z));
-        h.w = __fadd_rn(__fmul_rn(beta, zi.w), __fmul_rn(omb, acc[p].w));
-        *reinterpret_cast<float4*>(H + it.node * D + o) = h;
-      }
-    }
   }
 }
 
@@ -291,21 +292,9 @@ template <class M>
 int launch_attn(const DlGraphDev& g, long long n_items, const float* Z, float T, uint8_t* kstar,
                 float* w, float* s, float* hub_ws, cudaStream_t st) {
   int grid = 1;
-  int rc = dl_grid_for(k_edge_attn_fwd<M>, n_items, &grid);
+  int rc = dl_grid_for(k_edge_attn_fwd<M>, n_items, &grid, 0, DL_CTA_S);
   if (rc) return rc;
-  k_edge_attn_fwd<M><<<grid, DL_CTA, 0, st>>>(g, Z, T, kstar, w, s, hub_ws);
-  DL_LAUNCH_CHECK();
-  return DL_OK;
-}
-
-template <class M>
-int launch_spmm(const DlGraphDev& g, long long n_items, const float* Z, const uint8_t* kstar,
-                const float* w, const float* s, float beta, float omb, float* H, float* hub_ws,
-                cudaStream_t st) {
-  int grid = 1;
-  int rc = dl_grid_for(k_factor_spmm_fwd<M>, n_items, &grid);
-  if (rc) return rc;
-  k_factor_spmm_fwd<M><<<grid, DL_CTA, 0, st>>>(g, Z, kstar, w, s, beta, omb, H, hub_ws);
+  k_edge_attn_fwd<M><<<grid, DL_CTA_S, 0, st>>>(g, Z, T, kstar, w, s, hub_ws);
   DL_LAUNCH_CHECK();
   return DL_OK;
 }
@@ -337,9 +326,13 @@ int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float
   const DlGraphDev g = dl_graph_dev(g_host);
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
+  if (g.erow && g.nnz > 0 && !getenv("DL_NO_STREAM"))
+    rc = dl_launch_attn_stream(g, g.erow, Z, K, d, T, kstar, w, s, hub_ws, st);
+  if (rc == -1000) {
 #define BODY_MACRO(M) rc = launch_attn<M>(g, n_items, Z, T, kstar, w, s, hub_ws, st);
-  DL_DISPATCH_SHAPES()
+    DL_DISPATCH_SHAPES()
 #undef BODY_MACRO
+  }
   if (rc == -1000) {
     int grid = 1;
     rc = dl_grid_for(k_edge_attn_fwd_generic, n_items, &grid);
@@ -366,10 +359,8 @@ int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* ks
   cudaStream_t st = (cudaStream_t)stream;
   const DlGraphDev g = dl_graph_dev(g_host);
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
-  int rc = -1000;
-#define BODY_MACRO(M) rc = launch_spmm<M>(g, n_items, Z, kstar, w, s, beta, one_minus_beta, H, hub_ws, st);
-  DL_DISPATCH_SHAPES()
-#undef BODY_MACRO
+  int rc = dl_launch_slice_gather(0, g, n_items, Z, Z, kstar, w, s, K, d, beta, one_minus_beta, H, nullptr,
+                                  hub_ws, st);
   if (rc == -1000) {
     int grid = 1;
     rc = dl_grid_for(k_factor_spmm_fwd_generic, n_items, &grid);

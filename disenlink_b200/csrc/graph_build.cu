@@ -225,6 +225,15 @@ __global__ void k_hub_item_fill(const long long* __restrict__ seg_ptr, long long
   }
 }
 
+// ---- COO row array ---------------------------------------------------------------------------
+__global__ void k_entry_rows(const long long* __restrict__ rowptr, long long N, int* __restrict__ erow) {
+  int lane = threadIdx.x & 31;
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < N; r += nwarps)
+    for (long long e = rowptr[r] + lane; e < rowptr[r + 1]; e += 32) erow[e] = (int)r;
+}
+
 // ---- pair incidence ---------------------------------------------------------------------------
 // key = local row of the endpoint if it lies in [row_lo, row_hi), else the sentinel n_local (sorts
 // last and is dropped by the decode kernel)
@@ -345,6 +354,15 @@ int dl_csr_from_dense(const float* adj, int64_t N, int64_t* rowptr, int32_t* col
   }
   if (N > 0) {
     k_dense_fill<<<blocks_for(N * 32), 256, 0, st>>>(adj, N, (const long long*)rowptr, col);
+    DL_LAUNCH_CHECK();
+  }
+  return DL_OK;
+}
+
+int dl_entry_rows(const int64_t* rowptr, int64_t N, int64_t nnz, int32_t* erow, dl_stream_t stream) {
+  if (N < 0 || nnz < 0 || !rowptr || (nnz > 0 && !erow)) return DL_EINVAL;
+  if (N > 0 && nnz > 0) {
+    k_entry_rows<<<blocks_for(N * 32), 256, 0, (cudaStream_t)stream>>>((const long long*)rowptr, N, erow);
     DL_LAUNCH_CHECK();
   }
   return DL_OK;

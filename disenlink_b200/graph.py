@@ -126,9 +126,13 @@ class Graph:
                 check(L.dl_hub_items(ptr(self.rowptr), ptr(self.perm), self.n_hub,
                                      ptr(self.hub_seg_ptr), ptr(self.item_hub), self.n_hub_items,
                                      stream_of(dev)), "dl_hub_items(fill)")
+            # COO row array for the streaming kernels (4 bytes per entry)
+            self.erow = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+            check(L.dl_entry_rows(ptr(self.rowptr), N, self.nnz, ptr(self.erow), stream_of(dev)),
+                  "dl_entry_rows")
         self.struct = DlGraph(self.N, self.nnz, ptr(self.rowptr), ptr(self.col), ptr(self.perm),
                               self.n_hub, self.n_hub_items, ptr(self.hub_seg_ptr),
-                              ptr(self.item_hub), self.row_base)
+                              ptr(self.item_hub), ptr(self.erow), self.row_base)
         self._hub_ws = None
 
     @property

@@ -233,9 +233,9 @@ class PartitionedLinkStep:
         """weighted BCE over all pairs and dL/dlogit (every rank evaluates the full P-vector; it
         is P floats).  d/dlogit of BCE(sigmoid(S), y) = (p - y)."""
         p = self.prob
-        eps = 1e-12
-        self.loss = -(self.weights * (self.labels * torch.log(p.clamp_min(eps)) +
-                                      (1 - self.labels) * torch.log((1 - p).clamp_min(eps)))).sum()
+        # F.binary_cross_entropy semantics: log terms clamped at -100
+        self.loss = -(self.weights * (self.labels * torch.log(p).clamp_min(-100.0) +
+                                      (1 - self.labels) * torch.log(1 - p).clamp_min(-100.0))).sum()
         torch.sub(p, self.labels, out=self.dS)
         self.dS.mul_(self.weights)
         self.mark("loss")

@@ -95,6 +95,10 @@ int dl_degree_buckets(const int64_t* rowptr, int64_t N, int32_t* perm, int64_t* 
 int dl_hub_items(const int64_t* rowptr, const int32_t* perm, int64_t n_hub, int64_t* hub_seg_ptr,
                  int32_t* item_hub, int64_t n_items, dl_stream_t stream);
 
+/* erow[e] = row of entry e (the COO row array of the CSR).  The streaming kernels cut the entries
+ * into equal chunks regardless of row boundaries and read the row id per entry. */
+int dl_entry_rows(const int64_t* rowptr, int64_t N, int64_t nnz, int32_t* erow, dl_stream_t stream);
+
 /* Everything a kernel needs to walk the graph.  Plain-old-data, passed by pointer (host memory). */
 typedef struct dl_graph {
   int64_t N;                   /* rows held here (all nodes on one GPU; the owned range when the
@@ -107,6 +111,9 @@ typedef struct dl_graph {
   int64_t n_hub_items;         /* total segments of hub rows */
   const int64_t* hub_seg_ptr;  /* [n_hub+1] */
   const int32_t* item_hub;     /* [n_hub_items] */
+  const int32_t* erow;         /* [nnz] local row id of every entry (COO row array, from
+                                  dl_entry_rows); NULL = not built, the row-per-warp kernels are
+                                  used instead of the streaming ones */
   int64_t row_base;            /* global node id of local row 0: per-node arrays (Z, H, s, r, G,
                                   dZ) are indexed by row_base + row, i.e. they are full-size
                                   [N_global, ...] arrays of which this call reads every gathered
