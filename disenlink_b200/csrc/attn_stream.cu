@@ -266,11 +266,18 @@ int dl_launch_attn_stream(const DlGraphDev& g, const int* erow, const float* Z, 
   DL_DISPATCH_SHAPES()
 #undef BODY_MACRO
   if (rc != DL_OK) return rc;
-  const long long n_items = g.n_hub_items + (g.N - g.n_hub);
-  int grid = 1;
-  rc = dl_grid_for(k_row_sums, n_items, &grid);
+  rc = dl_launch_gather_stream(2, g, nullptr, nullptr, kstar, w, nullptr, K, d, 0.0f, 0.0f, s, nullptr, hub_ws,
+                               st);
+  if (rc == -1000) {
+    const long long n_items = g.n_hub_items + (g.N - g.n_hub);
+    int grid = 1;
+    rc = dl_grid_for(k_row_sums, n_items, &grid);
+    if (rc) return rc;
+    k_row_sums<<<grid, DL_CTA, 0, st>>>(g, kstar, w, K, s, hub_ws);
+    DL_LAUNCH_CHECK();
+    if (g.n_hub > 0) return -1001;   // caller runs the hub fix-up
+    rc = DL_OK;
+  }
   if (rc) return rc;
-  k_row_sums<<<grid, DL_CTA, 0, st>>>(g, kstar, w, K, s, hub_ws);
-  DL_LAUNCH_CHECK();
   return DL_OK;
 }

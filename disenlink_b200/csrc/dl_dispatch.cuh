@@ -98,3 +98,13 @@ int dl_launch_slice_gather(int mode, const DlGraphDev& g, long long n_items, con
 // streaming instantiation.
 int dl_launch_attn_stream(const DlGraphDev& g, const int* erow, const float* Z, int K, int d, float T,
                           unsigned char* kstar, float* w, float* s, float* hub_ws, cudaStream_t st);
+
+// Streaming slice gather with per-row register accumulators (gather_stream.cu).
+// mode 0: aggregation forward (SRC = Z, OUT = H); mode 1: backward pass 1 (SRC = G, OUT = dZ
+// accumulated, r written); mode 2: routed row sums (OUT = s).  Returns -1000 when (K, d) has no
+// streaming instantiation or the graph has no COO row array.
+size_t dl_gather_stream_scratch_floats(long long nnz, int mode, int K, int d);
+int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const float* SRC,
+                            const unsigned char* kstar, const float* w, const float* s, int K, int d,
+                            float beta, float omb, float* OUT, float* r, float* scratch,
+                            cudaStream_t st);

@@ -15,6 +15,8 @@
 // gathers can be issued together with the z_j gather.
 //
 // HBM bytes per entry (D=128, d=16): pass 1  4 + 5 + 64;  pass 2  4 + 1 + 512 + 64 + 4 + 4.
+#include <stdlib.h>
+
 #include "dl_dispatch.cuh"
 
 namespace {
@@ -394,8 +396,13 @@ int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
   cudaStream_t st = (cudaStream_t)stream;
   const DlGraphDev g = dl_graph_dev(g_host);
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
-  int rc = dl_launch_slice_gather(1, g, n_items, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r,
-                                  hub_ws, st);
+  int rc = -1000;
+  if (!getenv("DL_NO_STREAM"))
+    rc = dl_launch_gather_stream(1, g, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, hub_ws, st);
+  if (rc == DL_OK) return DL_OK;
+  if (rc != -1000) return rc;
+  rc = dl_launch_slice_gather(1, g, n_items, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r,
+                              hub_ws, st);
   if (rc == -1000) {
     int grid = 1;
     rc = dl_grid_for(k_factor_bwd_gather_generic, n_items, &grid);

@@ -312,7 +312,12 @@ extern "C" {
 
 size_t dl_hub_scratch_floats(const dl_graph* g_host, int64_t width) {
   if (!g_host || width < 0) return 0;
-  return (size_t)g_host->n_hub_items * (size_t)width;
+  // hub-segment partials of the row-per-warp kernels, or range carries + chain scratch of the
+  // streaming kernels (3 records per 2048-entry range), whichever is larger
+  const size_t hub = (size_t)g_host->n_hub_items * (size_t)width;
+  const long long RE = 2048;
+  const size_t stream = (size_t)((g_host->nnz + RE - 1) / RE) * 3 * (size_t)width;
+  return hub > stream ? hub : stream;
 }
 
 int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float T,
@@ -326,8 +331,11 @@ int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float
   const DlGraphDev g = dl_graph_dev(g_host);
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
-  if (g.erow && g.nnz > 0 && !getenv("DL_NO_STREAM"))
+  bool stream_tried = false;
+  if (g.erow && g.nnz > 0 && !getenv("DL_NO_STREAM")) {
     rc = dl_launch_attn_stream(g, g.erow, Z, K, d, T, kstar, w, s, hub_ws, st);
+    stream_tried = (rc != -1000);
+  }
   if (rc == -1000) {
 #define BODY_MACRO(M) rc = launch_attn<M>(g, n_items, Z, T, kstar, w, s, hub_ws, st);
     DL_DISPATCH_SHAPES()
@@ -341,8 +349,11 @@ int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float
     DL_LAUNCH_CHECK();
     rc = DL_OK;
   }
+  bool streamed = false;
+  if (rc == -1001) { rc = DL_OK; }           // streamed routing, row sums by the row-per-warp kernel
+  else if (rc == DL_OK && g.erow && g.nnz > 0 && !getenv("DL_NO_STREAM") && stream_tried) streamed = true;
   if (rc) return rc;
-  if (g.n_hub > 0) {
+  if (g.n_hub > 0 && !streamed) {
     k_attn_hub_fixup<<<fixup_blocks(g.n_hub * K), 256, 0, st>>>(g, K, hub_ws, s);
     DL_LAUNCH_CHECK();
   }
@@ -359,8 +370,13 @@ int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* ks
   cudaStream_t st = (cudaStream_t)stream;
   const DlGraphDev g = dl_graph_dev(g_host);
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
-  int rc = dl_launch_slice_gather(0, g, n_items, Z, Z, kstar, w, s, K, d, beta, one_minus_beta, H, nullptr,
-                                  hub_ws, st);
+  int rc = -1000;
+  if (!getenv("DL_NO_STREAM"))
+    rc = dl_launch_gather_stream(0, g, Z, Z, kstar, w, s, K, d, beta, one_minus_beta, H, nullptr, hub_ws, st);
+  if (rc == DL_OK) return DL_OK;             // carries, chained rows and empty rows all handled
+  if (rc != -1000) return rc;
+  rc = dl_launch_slice_gather(0, g, n_items, Z, Z, kstar, w, s, K, d, beta, one_minus_beta, H, nullptr,
+                              hub_ws, st);
   if (rc == -1000) {
     int grid = 1;
     rc = dl_grid_for(k_factor_spmm_fwd_generic, n_items, &grid);

@@ -1,0 +1,387 @@
+// gather_stream.cu -- streaming per-factor gather / segment-sum with per-row register accumulators.
+//
+//   MODE 0  aggregation forward  [ref: model.py:75]
+//           H[i,k] = beta Z[i,k] + (1-beta) sum_{e in row i, kstar=k} (w[e] / s[col_e,k]) Z[col_e,k]
+//   MODE 1  backward pass 1      [ref: autograd of model.py:70-75]
+//           T_[i,k] = (1-beta)/s[i,k] sum_{e in row i, kstar=k} w[e] G[col_e,k]
+//           r[i,k] = <Z[i,k],T_[i,k]>/s[i,k] ;  dZ[i] += beta G[i] + T_[i]
+//   MODE 2  routed row sums      [ref: model.py:70-72]
+//           s[i,k] = sum_{e in row i, kstar=k} w[e], zeros -> 1
+//
+// Same decomposition as attn_stream.cu: the CSR entries are cut into 32-entry chunks regardless of
+// row boundaries and every warp walks its own stream of chunks (ranges of 64 chunks), so the load
+// is balanced whatever the degree distribution.  Per chunk the warp
+//   - has the (row, col, kstar, w) of the chunk two ahead in flight (coalesced loads),
+//   - has the s[col,kstar] gather and the 32 routed slices (d floats each, cp.async into a private
+//     double-buffered shared-memory tile, 8 entries per instruction at d = 16) of the next chunk
+//     in flight,
+//   - walks the entries of the current chunk IN CSR ORDER, adding coef * slice into the accumulator
+//     of the current row (lane (k, g) owns chunk g of factor k, so only the routed factor's lanes
+//     work) and flushing it when the row id changes.
+// The accumulation order of a row is exactly its column order -- the same as the CPU oracle.
+// A row cut by a range boundary leaves its partial sums in a carry buffer (head / tail per range);
+// k_gather_chain sums the pieces of such rows in range order and applies the row epilogue, and
+// k_gather_empty_rows writes the rows that have no entries.  No atomics anywhere.
+#include "dl_dispatch.cuh"
+#include "dl_stream.cuh"
+
+namespace {
+
+constexpr int GS_WARPS = 16;   // warps per CTA
+
+// flat width of a row's accumulator / carry record
+__host__ __device__ constexpr int carry_width(int mode, int K, int d) { return mode == 2 ? K : K * d; }
+
+// ---- row epilogues on a flat accumulator held by one thread-strided warp (rare rows) ----------
+__device__ __forceinline__ void epilogue_flat(int mode, int lane, long long node, int K, int d,
+                                              const float* acc /* global or shared, flat */,
+                                              const float* __restrict__ Z, const float* __restrict__ G,
+                                              const float* __restrict__ s, float beta, float omb,
+                                              float* __restrict__ OUT, float* __restrict__ r) {
+  const long long D = (long long)K * d;
+  if (mode == 2) {
+    for (int k = lane; k < K; k += 32) {
+      const float v = acc ? acc[k] : 0.0f;
+      OUT[node * K + k] = (v == 0.0f) ? 1.0f : v;
+    }
+  } else if (mode == 0) {
+    for (long long x = lane; x < D; x += 32) {
+      const float v = acc ? acc[x] : 0.0f;
+      OUT[node * D + x] = __fadd_rn(__fmul_rn(beta, Z[node * D + x]), __fmul_rn(omb, v));
+    }
+  } else {
+    for (int k = 0; k < K; ++k) {
+      const float sk = s[node * K + k];
+      const float scale = __fdiv_rn(omb, sk);
+      float part = 0.0f;
+      for (int x = lane; x < d; x += 32) {
+        const long long o = node * D + (long long)k * d + x;
+        const float tv = __fmul_rn(scale, acc ? acc[(long long)k * d + x] : 0.0f);
+        part = __fmaf_rn(Z[o], tv, part);
+        OUT[o] = __fadd_rn(OUT[o], __fmaf_rn(beta, G[o], tv));
+      }
+      for (int o = 16; o > 0; o >>= 1) part = __fadd_rn(part, __shfl_xor_sync(DL_FULL, part, o));
+      if (lane == 0) r[node * K + k] = __fdiv_rn(part, sk);
+    }
+  }
+}
+
+// rows without entries never show up in the entry stream
+__global__ void __launch_bounds__(DL_CTA)
+k_gather_empty_rows(DlGraphDev g, int mode, int K, int d, const float* __restrict__ Z,
+                    const float* __restrict__ G, const float* __restrict__ s, float beta, float omb,
+                    float* __restrict__ OUT, float* __restrict__ r) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * DL_WARPS_PER_CTA + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * DL_WARPS_PER_CTA;
+  // a warp scans 32 rows at a time (coalesced rowptr reads) and handles the empty ones
+  for (long long r0 = warp0 * 32; r0 < g.N; r0 += nwarps * 32) {
+    const long long row = r0 + lane;
+    const bool empty = row < g.N && __ldg(g.rowptr + row) == __ldg(g.rowptr + row + 1);
+    unsigned m = __ballot_sync(DL_FULL, empty);
+    while (m) {
+      const int l = __ffs(m) - 1;
+      m &= m - 1;
+      epilogue_flat(mode, lane, g.row_base + r0 + l, K, d, nullptr, Z, G, s, beta, omb, OUT, r);
+    }
+  }
+}
+
+// rows cut by range boundaries: sum the pieces in range order, then the epilogue.
+// carry layout: [range][0 = head, 1 = tail][W]
+__global__ void __launch_bounds__(DL_CTA)
+k_gather_chain(DlGraphDev g, int mode, int K, int d, const float* __restrict__ carry,
+               const float* __restrict__ Z, const float* __restrict__ G, const float* __restrict__ s,
+               float beta, float omb, float* __restrict__ OUT, float* __restrict__ r,
+               float* __restrict__ scratch /* [n_ranges][W] */) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * DL_WARPS_PER_CTA + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * DL_WARPS_PER_CTA;
+  const int W = carry_width(mode, K, d);
+  const long long RE = (long long)DL_CH * DL_RANGE;            // entries per range
+  const long long n_ranges = (g.nnz + RE - 1) / RE;
+  for (long long b = warp0; b < n_ranges; b += nwarps) {
+    const long long R1 = min((b + 1) * RE, g.nnz);
+    if (R1 >= g.nnz) continue;                                  // nothing after the last range
+    const int row = __ldg(g.erow + R1 - 1);
+    if (__ldg(g.erow + R1) != row) continue;                    // no row crosses this boundary
+    if (__ldg(g.rowptr + row) < b * RE) continue;               // the chain started in an earlier range
+    const long long last = (__ldg(g.rowptr + row + 1) - 1) / RE;   // range holding the row's last entry
+    float* acc = scratch + b * W;
+    for (int x = lane; x < W; x += 32) {
+      float v = carry[(b * 2 + 1) * W + x];                     // tail of the first range
+      for (long long bb = b + 1; bb <= last; ++bb) v = __fadd_rn(v, carry[(bb * 2) * W + x]);
+      acc[x] = v;
+    }
+    __syncwarp();
+    epilogue_flat(mode, lane, g.row_base + row, K, d, acc, Z, G, s, beta, omb, OUT, r);
+  }
+}
+
+// ---- the streaming kernel -----------------------------------------------------------------
+template <class M, int MODE>
+struct GatherStreamCfg {
+  static constexpr int SLB = M::d * 4;                                  // bytes of one routed slice
+  static constexpr int TILE_B = (MODE == 2) ? 0 : DL_CH * SLB;          // one chunk of slices
+  static constexpr size_t SMEM = (size_t)GS_WARPS * 2 * TILE_B;
+};
+
+template <class M, int MODE>
+__global__ void __launch_bounds__(GS_WARPS * 32)
+k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restrict__ SRC,
+                const unsigned char* __restrict__ kstar, const float* __restrict__ w,
+                const float* __restrict__ s, float beta, float omb, float* __restrict__ OUT,
+                float* __restrict__ r, float* __restrict__ carry) {
+  using C = GatherStreamCfg<M, MODE>;
+  constexpr int K = M::K, d = M::d, D = M::D, NP = M::NP, L = M::L, LP = M::LP, FPP = M::FPP;
+  constexpr int NG = 32 / LP, SLB = C::SLB, TILE_B = C::TILE_B;
+  constexpr int W = (MODE == 2) ? K : D;
+  extern __shared__ __align__(128) unsigned char dl_smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* tile = dl_smem_raw + (size_t)warp * 2 * TILE_B;
+  const long long gw = (long long)blockIdx.x * GS_WARPS + warp;
+  const int grp = lane / LP, gg = lane % LP, slot = M::slot(lane);
+  const bool glane = gg < L;
+  const long long RE = (long long)DL_CH * DL_RANGE;
+
+  DlChunkStream cs;
+  cs.init(g.nnz, (long long)gridDim.x * GS_WARPS);
+
+  struct Meta { int row, col, ks; float wv; };
+  auto load_meta = [&](long long cc, Meta& m) {
+    m.row = -1; m.col = 0; m.ks = 255; m.wv = 0.0f;
+    if (cc >= 0) {
+      const long long e = cc * DL_CH + lane;
+      if (e < g.nnz) {
+        m.row = __ldg(g.erow + e);
+        m.ks = __ldg(kstar + e);
+        m.wv = __ldg(w + e);
+        if (MODE != 2) m.col = __ldg(g.col + e);
+      }
+    }
+  };
+  auto issue_slices = [&](unsigned char* buf, const Meta& m) {
+    if (MODE == 2) return;
+#pragma unroll
+    for (int rd = 0; rd < LP; ++rd) {
+      const int idx = rd * NG + grp;
+      const int cc = __shfl_sync(DL_FULL, m.col, idx);
+      const int kk = __shfl_sync(DL_FULL, m.ks, idx);
+      if (glane && kk < K)
+        dl_cp_async16(buf + idx * SLB + gg * 16, SRC + (long long)cc * D + kk * d + gg * 4);
+    }
+  };
+
+  // accumulator of the current row: lane (slot, g) owns chunk g of factor p*FPP+slot (MODE 0/1);
+  // lane k owns factor k (MODE 2)
+  float4 acc[NP];
+  float acc2 = 0.0f;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) acc[p] = dl_zero4();
+  int cur_row = -1;
+  bool first_run = true;          // no flush yet in the current range
+  bool head_open = false, tail_open = false;
+  long long cur_range = -1;
+
+  auto flush = [&](bool at_range_end) {
+    if (cur_row >= 0) {
+      const bool to_head = first_run && head_open;
+      const bool to_tail = !to_head && at_range_end && tail_open;
+      if (to_head || to_tail) {
+        float* dst = carry + (cur_range * 2 + (to_tail ? 1 : 0)) * W;
+        if (MODE == 2) {
+          if (lane < K) dst[lane] = acc2;
+        } else {
+#pragma unroll
+          for (int p = 0; p < NP; ++p)
+            if (M::active(lane, p)) *reinterpret_cast<float4*>(dst + M::offset(lane, p)) = acc[p];
+        }
+      } else {
+        const long long node = g.row_base + cur_row;
+        if (MODE == 2) {
+          if (lane < K) OUT[node * K + lane] = (acc2 == 0.0f) ? 1.0f : acc2;
+        } else if (MODE == 0) {
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            if (!M::active(lane, p)) continue;
+            const int o = M::offset(lane, p);
+            const float4 zi = dl_ldg4(Z + node * D + o);
+            float4 h;
+            h.x = __fadd_rn(__fmul_rn(beta, zi.x), __fmul_rn(omb, acc[p].x));
+            h.y = __fadd_rn(__fmul_rn(beta, zi.y), __fmul_rn(omb, acc[p].y));
+            h.z = __fadd_rn(__fmul_rn(beta, zi.z), __fmul_rn(omb, acc[p].z));
+            h.w = __fadd_rn(__fmul_rn(beta, zi.w), __fmul_rn(omb, acc[p].w));
+            *reinterpret_cast<float4*>(OUT + node * D + o) = h;
+          }
+        } else {
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            const int k = M::factor(lane, p);
+            const bool act = M::active(lane, p);
+            const int o = M::offset(lane, p);
+            const float sk = (k < K) ? __ldg(s + node * K + k) : 1.0f;
+            const float scale = __fdiv_rn(omb, sk);
+            float4 tv;
+            tv.x = __fmul_rn(scale, acc[p].x); tv.y = __fmul_rn(scale, acc[p].y);
+            tv.z = __fmul_rn(scale, acc[p].z); tv.w = __fmul_rn(scale, acc[p].w);
+            const float4 zi = act ? dl_ldg4(Z + node * D + o) : dl_zero4();
+            const float dotzt = dl_group_sum<M>(dl_chunk_dot(zi, tv));
+            if (k < K && gg == 0) r[node * K + k] = __fdiv_rn(dotzt, sk);
+            if (act) {
+              const float4 gi = dl_ldg4(SRC + node * D + o);
+              float4* dp = reinterpret_cast<float4*>(OUT + node * D + o);
+              float4 cur = *dp;
+              cur.x = __fadd_rn(cur.x, __fmaf_rn(beta, gi.x, tv.x));
+              cur.y = __fadd_rn(cur.y, __fmaf_rn(beta, gi.y, tv.y));
+              cur.z = __fadd_rn(cur.z, __fmaf_rn(beta, gi.z, tv.z));
+              cur.w = __fadd_rn(cur.w, __fmaf_rn(beta, gi.w, tv.w));
+              *dp = cur;
+            }
+          }
+        }
+      }
+    }
+    if (cur_row >= 0) first_run = false;     // only a real run consumes the "first run of the range" slot
+    cur_row = -1;
+    acc2 = 0.0f;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[p] = dl_zero4();
+  };
+
+  long long c = cs.first(gw);
+  Meta mA, mB, mC;
+  load_meta(c, mA);
+  long long cn = cs.next(c);
+  load_meta(cn, mB);
+  float sjA = 1.0f, sjB = 1.0f;
+  if (MODE == 0 && mA.ks != 255) sjA = __ldg(s + (long long)mA.col * K + mA.ks);
+  int buf = 0;
+  issue_slices(tile, mA);
+  dl_cp_async_commit();
+
+  while (c >= 0) {
+    // pipeline: metadata two chunks ahead, s gather + slices one chunk ahead
+    const long long cnn = cs.next(cn);
+    load_meta(cnn, mC);
+    if (MODE == 0 && mB.ks != 255) sjB = __ldg(s + (long long)mB.col * K + mB.ks);
+    issue_slices(tile + (buf ^ 1) * TILE_B, mB);
+    dl_cp_async_commit();
+    dl_cp_async_wait<1>();
+    __syncwarp();
+
+    // range bookkeeping
+    const long long rg = c / DL_RANGE;
+    if (rg != cur_range) {
+      if (cur_range >= 0) flush(true);
+      cur_range = rg;
+      first_run = true;
+      const long long R0 = rg * RE, R1 = min(R0 + RE, g.nnz);
+      head_open = R0 > 0 && __ldg(g.erow + R0 - 1) == __ldg(g.erow + R0);
+      tail_open = R1 < g.nnz && __ldg(g.erow + R1) == __ldg(g.erow + R1 - 1);
+    }
+
+    const float coefA = (MODE == 0) ? __fdiv_rn(mA.wv, sjA) : mA.wv;
+    const unsigned vmask = __ballot_sync(DL_FULL, mA.row >= 0);
+    const int cnt = __popc(vmask);
+    const unsigned char* sl = tile + buf * TILE_B;
+    for (int idx = 0; idx < cnt; ++idx) {
+      const int re = __shfl_sync(DL_FULL, mA.row, idx);
+      const int ke = __shfl_sync(DL_FULL, mA.ks, idx);
+      const float cf = __shfl_sync(DL_FULL, coefA, idx);
+      if (re != cur_row) {                      // warp-uniform
+        flush(false);
+        cur_row = re;
+      }
+      if (MODE == 2) {
+        if (lane == ke) acc2 = __fadd_rn(acc2, cf);
+      } else {
+        if (glane && (ke % FPP) == slot) {
+          const float4 v = dl_lds4(sl + idx * SLB + gg * 16);
+          const int pe = ke / FPP;
+#pragma unroll
+          for (int p = 0; p < NP; ++p)
+            if (pe == p) dl_fma4(acc[p], cf, v);
+        }
+      }
+    }
+    __syncwarp();
+    buf ^= 1;
+    c = cn; cn = cnn;
+    mA = mB; mB = mC;
+    sjA = sjB;
+  }
+  if (cur_range >= 0) flush(true);
+  dl_cp_async_wait<0>();
+}
+
+template <class M, int MODE>
+int launch_gather_stream(const DlGraphDev& g, const float* Z, const float* SRC,
+                         const unsigned char* kstar, const float* w, const float* s, float beta,
+                         float omb, float* OUT, float* r, float* carry, cudaStream_t st) {
+  using C = GatherStreamCfg<M, MODE>;
+  if (C::SMEM > 200 * 1024) return -1000;
+  if (C::SMEM > 48 * 1024)
+    DL_CUDA_TRY(cudaFuncSetAttribute(k_gather_stream<M, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)C::SMEM));
+  int dev = 0, sms = 0, per_sm = 0;
+  DL_CUDA_TRY(cudaGetDevice(&dev));
+  DL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gather_stream<M, MODE>, GS_WARPS * 32,
+                                                            C::SMEM));
+  if (per_sm < 1) per_sm = 1;
+  const long long n_chunks = (g.nnz + DL_CH - 1) / DL_CH;
+  const long long n_ranges = (n_chunks + DL_RANGE - 1) / DL_RANGE;
+  long long grid = (n_ranges + GS_WARPS - 1) / GS_WARPS;
+  const long long cap = (long long)sms * per_sm;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  k_gather_stream<M, MODE><<<(int)grid, GS_WARPS * 32, C::SMEM, st>>>(g, Z, SRC, kstar, w, s, beta, omb, OUT,
+                                                                     r, carry);
+  DL_LAUNCH_CHECK();
+  return DL_OK;
+}
+
+inline int small_grid(long long n_warps_wanted) {
+  long long b = (n_warps_wanted + DL_WARPS_PER_CTA - 1) / DL_WARPS_PER_CTA;
+  if (b < 1) b = 1;
+  if (b > 148 * 8) b = 148 * 8;
+  return (int)b;
+}
+
+}  // namespace
+
+// floats of scratch the streaming gather needs: carries [n_ranges][2][W] + chain scratch [n_ranges][W]
+size_t dl_gather_stream_scratch_floats(long long nnz, int mode, int K, int d) {
+  const long long RE = (long long)DL_CH * DL_RANGE;
+  const long long n_ranges = (nnz + RE - 1) / RE;
+  return (size_t)n_ranges * 3 * (size_t)carry_width(mode, K, d);
+}
+
+// mode 0 / 1 / 2 as above; returns -1000 when (K, d) has no streaming instantiation.
+// scratch: dl_gather_stream_scratch_floats floats.
+int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const float* SRC,
+                            const unsigned char* kstar, const float* w, const float* s, int K, int d,
+                            float beta, float omb, float* OUT, float* r, float* scratch,
+                            cudaStream_t st) {
+  if (!g.erow || g.nnz == 0 || !scratch) return -1000;
+  const long long RE = (long long)DL_CH * DL_RANGE;
+  const long long n_ranges = (g.nnz + RE - 1) / RE;
+  const int W = carry_width(mode, K, d);
+  float* carry = scratch;
+  float* chain = scratch + (size_t)n_ranges * 2 * W;
+  int rc = -1000;
+#define BODY_MACRO(M)                                                                                       \
+  rc = (mode == 0)   ? launch_gather_stream<M, 0>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, st)     \
+       : (mode == 1) ? launch_gather_stream<M, 1>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, st)     \
+                     : launch_gather_stream<M, 2>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, st);
+  DL_DISPATCH_SHAPES()
+#undef BODY_MACRO
+  if (rc != DL_OK) return rc;
+  k_gather_chain<<<small_grid(n_ranges), DL_CTA, 0, st>>>(g, mode, K, d, carry, Z, SRC, s, beta, omb, OUT, r,
+                                                          chain);
+  DL_LAUNCH_CHECK();
+  k_gather_empty_rows<<<small_grid((g.N + 31) / 32), DL_CTA, 0, st>>>(g, mode, K, d, Z, SRC, s, beta, omb,
+                                                                     OUT, r);
+  DL_LAUNCH_CHECK();
+  return DL_OK;
+}

@@ -141,7 +141,7 @@ class Graph:
 
     def hub_scratch(self, width: int):
         """fp32 scratch for hub-row partials of `width` floats per segment (None if no hubs)."""
-        need = self.n_hub_items * int(width)
+        need = int(lib().dl_hub_scratch_floats(self.ref, int(width)))
         if need == 0:
             return None
         if self._hub_ws is None or self._hub_ws.numel() < need:
