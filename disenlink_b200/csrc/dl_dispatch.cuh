@@ -108,3 +108,10 @@ int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const
                             const unsigned char* kstar, const float* w, const float* s, int K, int d,
                             float beta, float omb, float* OUT, float* r, float* scratch,
                             cudaStream_t st);
+int dl_gather_chain_add(const DlGraphDev& g, int K, int d, float* scratch, float* OUT, cudaStream_t st);
+
+// Streaming backward pass 2 (bwd_stream.cu).  Returns -1000 when (K, d) has no streaming
+// instantiation.
+int dl_launch_bwd_edges_stream(const DlGraphDev& g, const float* Z, const float* G,
+                               const unsigned char* kstar, const float* s, const float* r, int K, int d,
+                               float omb, float T, float* dZ, float* scratch, cudaStream_t st);

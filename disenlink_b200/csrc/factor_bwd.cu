@@ -436,6 +436,10 @@ int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   const long long D = (long long)K * d;
   int rc = -1000;
+  if (!getenv("DL_NO_STREAM"))
+    rc = dl_launch_bwd_edges_stream(g, Z, G, kstar, s, r, K, d, one_minus_beta, T, dZ, hub_ws, st);
+  if (rc == DL_OK) return DL_OK;
+  if (rc != -1000) return rc;
 #define BODY_MACRO(M) \
   rc = launch_bwd_edges<M>(g, n_items, Z, G, kstar, s, r, one_minus_beta, T, dZ, hub_ws, st);
   DL_DISPATCH_SHAPES()

@@ -39,7 +39,10 @@ __device__ __forceinline__ void epilogue_flat(int mode, int lane, long long node
                                               const float* __restrict__ s, float beta, float omb,
                                               float* __restrict__ OUT, float* __restrict__ r) {
   const long long D = (long long)K * d;
-  if (mode == 2) {
+  if (mode == 3) {                       // plain accumulate (backward pass 2 partial sums)
+    if (acc)
+      for (long long x = lane; x < D; x += 32) OUT[node * D + x] = __fadd_rn(OUT[node * D + x], acc[x]);
+  } else if (mode == 2) {
     for (int k = lane; k < K; k += 32) {
       const float v = acc ? acc[k] : 0.0f;
       OUT[node * K + k] = (v == 0.0f) ? 1.0f : v;
@@ -382,6 +385,17 @@ int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const
   DL_LAUNCH_CHECK();
   k_gather_empty_rows<<<small_grid((g.N + 31) / 32), DL_CTA, 0, st>>>(g, mode, K, d, Z, SRC, s, beta, omb,
                                                                      OUT, r);
+  DL_LAUNCH_CHECK();
+  return DL_OK;
+}
+
+// chain fix-up alone, adding the stitched partial sums into OUT (used by bwd_stream.cu)
+int dl_gather_chain_add(const DlGraphDev& g, int K, int d, float* scratch, float* OUT, cudaStream_t st) {
+  const long long RE = (long long)DL_CH * DL_RANGE;
+  const long long n_ranges = (g.nnz + RE - 1) / RE;
+  const int W = K * d;
+  k_gather_chain<<<small_grid(n_ranges), DL_CTA, 0, st>>>(g, 3, K, d, scratch, nullptr, nullptr, nullptr, 0.0f,
+                                                          0.0f, OUT, nullptr, scratch + (size_t)n_ranges * 2 * W);
   DL_LAUNCH_CHECK();
   return DL_OK;
 }
