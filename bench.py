@@ -313,10 +313,12 @@ def run_native(args):
     sampler.start()
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.profiler.start()      # ncu --profile-from-start off captures exactly the timed steps
     ev_a.record(torch.cuda.current_stream(dev))
     for _ in range(args.steps):
         step.run(Z)
     ev_b.record(torch.cuda.current_stream(dev))
+    torch.cuda.profiler.stop()
     barrier()
     clocks = sampler.stop()
     abi_calls = _lib.launches - launches0
@@ -350,7 +352,10 @@ def run_native(args):
     # node-major decoder backward: per incidence the other endpoint's Z and H rows + 3 ids/floats,
     # per node 2 rows in and 2 rows out (less than SURVEY's scatter-form P*(32D+16): see DESIGN.md)
     ab["pair_bwd"] = int(step.inc.nnz) * (8 * D + 12) + part.n_local * 16 * D
-    launches_per_step = 6 + (4 if step.graph.n_hub > 0 else 0) + (1 if step.inc.n_hub > 0 else 0)
+    # kernels of libdisenlink_b200.so per step (streaming path): attention = routing + row sums +
+    # chain + empty rows (4); aggregation = gather + chain + empty rows (3); pair scoring fwd (1);
+    # decoder backward (1, +1 hub fix-up); backward pass 1 (3); backward pass 2 = stream + chain (2)
+    launches_per_step = 14 + (1 if step.inc.n_hub > 0 else 0)
     kernels = {}
     for kname in KERNEL_PHASES:
         ms = phase_ms[kname]

@@ -20,16 +20,18 @@
 
 namespace {
 
+constexpr int AT_RING = 2;   // stages per warp ring: one in flight while one is consumed (32 warps/SM)
+
 template <class M>
 struct AttnStreamCfg {
   static constexpr int ROWB = M::D * 4;                           // bytes of one node row
   static constexpr int STAGE_B = (DL_HS + DL_OWNQ) * ROWB;        // neighbour rows + own-row slots
   static constexpr int BUDGET = 200 * 1024;
-  static constexpr int NW_RAW = BUDGET / (DL_RING * STAGE_B);
+  static constexpr int NW_RAW = BUDGET / (AT_RING * STAGE_B);
   static constexpr bool OK = NW_RAW >= 4;                         // else: row-per-warp kernels
-  static constexpr int NW = NW_RAW >= 24 ? 24 : (OK ? NW_RAW : 4);   // warps per CTA
+  static constexpr int NW = NW_RAW >= 32 ? 32 : (OK ? NW_RAW : 4);   // warps per CTA
   static constexpr int THREADS = NW * 32;
-  static constexpr size_t SMEM = (size_t)NW * DL_RING * STAGE_B;
+  static constexpr size_t SMEM = (size_t)NW * AT_RING * STAGE_B;
 };
 
 // cp.async one node row (ROWB bytes) into shared memory, all 32 lanes cooperating
@@ -78,7 +80,7 @@ k_attn_stream(DlGraphDev g, const int* __restrict__ erow, const float* __restric
   constexpr int SUBS = DL_HS / EB;   // sub-blocks per stage
   extern __shared__ __align__(128) unsigned char dl_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* ring = dl_smem_raw + (size_t)warp * DL_RING * STAGE_B;
+  unsigned char* ring = dl_smem_raw + (size_t)warp * AT_RING * STAGE_B;
   const long long gw = (long long)blockIdx.x * C::NW + warp;
 
   int off[NP];
@@ -104,10 +106,11 @@ k_attn_stream(DlGraphDev g, const int* __restrict__ erow, const float* __restric
   load_meta(c, rowA, colA);
   long long cn = cs.next(c);
   load_meta(cn, rowB, colB);
-  dl_issue_stage<M>(ring, Z, g.row_base, rowA, colA, 0, lane);
-  dl_cp_async_commit();
-  dl_issue_stage<M>(ring + STAGE_B, Z, g.row_base, rowA, colA, 1, lane);
-  dl_cp_async_commit();
+#pragma unroll
+  for (int pq = 0; pq < AT_RING - 1; ++pq) {
+    dl_issue_stage<M>(ring + pq * STAGE_B, Z, g.row_base, rowA, colA, pq, lane);
+    dl_cp_async_commit();
+  }
   int slot = 0;   // ring slot of the stage about to be consumed
 
   while (c >= 0) {
@@ -123,13 +126,15 @@ k_attn_stream(DlGraphDev g, const int* __restrict__ erow, const float* __restric
     const unsigned vmaskA = __ballot_sync(DL_FULL, rowA >= 0);
 #pragma unroll
     for (int q = 0; q < DL_QPC; ++q) {
-      // keep two stages in flight: issue the stage two ahead of the one consumed now
-      int islot = slot + 2;
-      if (islot >= DL_RING) islot -= DL_RING;
-      if (q < DL_QPC - 2) dl_issue_stage<M>(ring + islot * STAGE_B, Z, g.row_base, rowA, colA, q + 2, lane);
-      else dl_issue_stage<M>(ring + islot * STAGE_B, Z, g.row_base, rowB, colB, q + 2 - DL_QPC, lane);
+      // keep AT_RING-1 stages in flight: issue the stage that far ahead of the one consumed now
+      int islot = slot + (AT_RING - 1);
+      if (islot >= AT_RING) islot -= AT_RING;
+      if (q < DL_QPC - (AT_RING - 1))
+        dl_issue_stage<M>(ring + islot * STAGE_B, Z, g.row_base, rowA, colA, q + (AT_RING - 1), lane);
+      else
+        dl_issue_stage<M>(ring + islot * STAGE_B, Z, g.row_base, rowB, colB, q + (AT_RING - 1) - DL_QPC, lane);
       dl_cp_async_commit();
-      dl_cp_async_wait<DL_RING - 1>();
+      dl_cp_async_wait<AT_RING - 1>();
       __syncwarp();
       const unsigned char* st = ring + slot * STAGE_B;
       const int cnt = __popc((vmaskA >> (q * DL_HS)) & ((1u << DL_HS) - 1u));
@@ -193,7 +198,7 @@ k_attn_stream(DlGraphDev g, const int* __restrict__ erow, const float* __restric
         if (q * SUBS + sb == lane / EB) { out_ks = ks; out_w = wv; }
       }
       __syncwarp();   // every lane is done with this stage before it is refilled
-      slot = (slot + 1 == DL_RING) ? 0 : slot + 1;
+      slot = (slot + 1 == AT_RING) ? 0 : slot + 1;
     }
     {
       const int oi = (lane & ~(EB - 1)) + my_e;

@@ -1,0 +1,127 @@
+"""GPU tests of the drop-in module API (disenlink_b200.model) against the reference's own outputs
+(golden vectors produced by /root/reference/model.py): same constructor, state_dict and forward
+contract as model.py:91-114, dense [N,N] link_pred for a dense adj, LinkScorer for a Graph."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def dense_adj_sym(src, dst, n):
+    adj = torch.zeros(n, n)
+    adj[torch.as_tensor(src), torch.as_tensor(dst)] = 1
+    adj = adj + adj.t()
+    adj[adj != 0] = 1
+    return adj
+
+
+def build(g):
+    from disenlink_b200.model import Disentangle
+    m = Disentangle(int(g["F"]), int(g["nhid"]), int(g["d"]), nfactor=int(g["K"]), beta=float(g["beta"]), t=1)
+    m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g if k.startswith("sd.")}, strict=True)
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("fixture", ["module_small", "module_nhid1"])
+def test_forward_matches_reference_dense_contract(fixture):
+    g = load_golden(fixture)
+    n = int(g["N"])
+    m = build(g)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    adj = dense_adj_sym(g["src"], g["dst"], n).to(DEV)
+    H, link_pred = m(x, adj)
+    assert tuple(H.shape) == (n, int(g["K"]) * int(g["d"])) and tuple(link_pred.shape) == (n, n)
+    assert relerr(H.detach().cpu().numpy(), g["ref_H"]) < TOL
+    assert relerr(link_pred.detach().cpu().numpy(), g["ref_link_pred"]) < TOL
+    # second call hits the cached graph and is bitwise identical
+    H2, lp2 = m(x, adj)
+    assert torch.equal(H, H2) and torch.equal(link_pred, lp2)
+
+
+def test_training_step_gradients_match_reference():
+    g = load_golden("module_small")
+    n = int(g["N"])
+    m = build(g)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    adj = dense_adj_sym(g["src"], g["dst"], n).to(DEV)
+    pu, pv = torch.from_numpy(g["pu"]).to(DEV), torch.from_numpy(g["pv"]).to(DEV)
+    lab = torch.from_numpy(g["lab"]).to(DEV)
+    # (a) the unmodified script's way: index the dense link_pred
+    H, link_pred = m(x, adj)
+    loss = F.binary_cross_entropy(link_pred[pu, pv], lab)
+    loss.backward()
+    assert abs(loss.item() - float(g["ref_loss"])) < TOL * abs(float(g["ref_loss"]))
+    grads_dense = {k: p.grad.detach().cpu().numpy().copy() for k, p in m.named_parameters()}
+    for k, gr in grads_dense.items():
+        assert relerr(gr, g["grad." + k]) < 5 * TOL, k
+    # (b) the scalable way: Graph handle + LinkScorer on the pair list
+    from disenlink_b200.graph import Graph
+    m.zero_grad()
+    graph = Graph.from_edges(torch.from_numpy(g["src"]).to(DEV), torch.from_numpy(g["dst"]).to(DEV), n)
+    H2, scorer = m(x, graph)
+    loss2 = F.binary_cross_entropy(scorer(torch.stack([pu, pv])), lab)
+    loss2.backward()
+    assert abs(loss2.item() - float(g["ref_loss"])) < TOL * abs(float(g["ref_loss"]))
+    for k, p in m.named_parameters():
+        assert relerr(p.grad.cpu().numpy(), g["grad." + k]) < 5 * TOL, k
+    # boolean-mask indexing of the scorer follows the script's row-major order
+    mask = torch.zeros(n, n, dtype=torch.bool, device=DEV)
+    mask[pu, pv] = True
+    assert relerr(scorer[mask].detach().cpu().numpy(), link_pred[mask].detach().cpu().numpy()) < TOL
+
+
+def test_disentangle_layer_returns_reference_triplet():
+    """Disentangle_layer.forward -> (h_list, alpha0 [K,N,N], att list), model.py:49-77."""
+    from disenlink_b200.model import Disentangle_layer
+    g = load_golden("tiny_generic")
+    n, K, d = int(g["N"]), int(g["K"]), int(g["d"])
+    Z = torch.from_numpy(g["Z"]).to(DEV)
+    adj = dense_adj_sym(g["src"], g["dst"], n).to(DEV)
+    layer = Disentangle_layer(K, float(g["beta"]), t=float(g["T"]))
+    h_list, alpha0, att = layer([Z[:, k, :] for k in range(K)], adj)
+    H = torch.cat(h_list, dim=1).cpu().numpy()
+    assert relerr(H, g["ref_H"]) < TOL
+    rows, cols = g["ref_rows"], g["ref_cols"]
+    att_st = torch.stack(att, 0).cpu().numpy()
+    assert relerr(att_st[g["ref_kstar"], rows, cols], g["ref_att"]) < TOL
+    off = att_st.copy()
+    off[g["ref_kstar"], rows, cols] = 0
+    assert np.abs(off).max() == 0.0
+    Zc = g["Z"].astype(np.float64)
+    want = np.exp(np.einsum("ikd,jkd->kij", Zc, Zc) / float(g["T"]))
+    assert relerr(alpha0.cpu().numpy(), want) < TOL
+
+
+def test_link_bce_loss_matches_script_semantics():
+    """ops.link_bce_loss == main_disentangled.py:195 on the chameleon fixture (pairs exactly once,
+    mean BCE, negatives / m), loss and dL/dZ."""
+    from disenlink_b200 import ops
+    from disenlink_b200.graph import Graph
+    g = load_golden("chameleon_K5_d32")
+    n, beta, T, m = int(g["N"]), float(g["beta"]), float(g["T"]), float(g["m"])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    graph = Graph.from_edges(t(g["src"]), t(g["dst"]), n)
+    pu, pv = ops.pairs_exactly_once(t(g["loss_pos_u"]), t(g["loss_pos_v"]), n)
+    nu, nv = ops.pairs_exactly_once(t(g["loss_neg_u"]), t(g["loss_neg_v"]), n)
+    batch = ops.PairBatch(torch.cat([pu, nu]), torch.cat([pv, nv]), n)
+    lab = torch.cat([torch.ones(pu.numel()), torch.zeros(nu.numel())]).to(DEV)
+    wts = torch.cat([torch.full((pu.numel(),), 1.0 / pu.numel()),
+                     torch.full((nu.numel(),), 1.0 / (m * nu.numel()))]).to(DEV)
+    Z = t(g["Z"]).requires_grad_(True)
+    loss, prob, H = ops.link_bce_loss(Z, graph, batch, lab, wts, beta, T)
+    loss.backward()
+    assert abs(loss.item() - float(g["ref_loss"])) < TOL * abs(float(g["ref_loss"]))
+    assert relerr(Z.grad.cpu().numpy(), g["ref_dZ"]) < 5 * TOL
+    assert relerr(H.cpu().numpy().reshape(n, -1), g["ref_H"]) < TOL
