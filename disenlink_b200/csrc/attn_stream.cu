@@ -78,6 +78,7 @@ k_attn_stream(DlGraphDev g, const int* __restrict__ erow, const float* __restric
   constexpr int K = M::K, D = M::D, NP = M::NP, EB = M::EB, LP = M::LP, FPP = M::FPP;
   constexpr int ROWB = C::ROWB, STAGE_B = C::STAGE_B;
   constexpr int SUBS = DL_HS / EB;   // sub-blocks per stage
+  constexpr bool DENSE = (M::L == M::LP) && (M::K % M::FPP == 0);   // every lane active in every pass
   extern __shared__ __align__(128) unsigned char dl_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* ring = dl_smem_raw + (size_t)warp * AT_RING * STAGE_B;
@@ -124,6 +125,7 @@ k_attn_stream(DlGraphDev g, const int* __restrict__ erow, const float* __restric
     const unsigned qbits = ((1u << DL_HS) - 1u) << ((lane / DL_HS) * DL_HS);
     const int rankA = __popc(smaskA & qbits & lane_le) - 1;
     const unsigned vmaskA = __ballot_sync(DL_FULL, rowA >= 0);
+    const bool allownA = __all_sync(DL_FULL, rankA < DL_OWNQ);
 #pragma unroll
     for (int q = 0; q < DL_QPC; ++q) {
       // keep AT_RING-1 stages in flight: issue the stage that far ahead of the one consumed now
@@ -139,30 +141,55 @@ k_attn_stream(DlGraphDev g, const int* __restrict__ erow, const float* __restric
       const unsigned char* st = ring + slot * STAGE_B;
       const int cnt = __popc((vmaskA >> (q * DL_HS)) & ((1u << DL_HS) - 1u));
       for (int sb = 0; sb * EB < cnt; ++sb) {
-        int rk[EB], rw[EB];
-#pragma unroll
-        for (int e = 0; e < EB; ++e) {
-          rk[e] = __shfl_sync(DL_FULL, rankA, q * DL_HS + sb * EB + e);
-          rw[e] = __shfl_sync(DL_FULL, rowA, q * DL_HS + sb * EB + e);
-        }
         float ev[NP];
+        // fast path: a full sub-block whose own rows are all staged (the common case) needs no
+        // per-entry validity handling; DENSE shapes (every lane owns a chunk) need no lane predicate
+        const bool full = allownA && (cnt - sb * EB >= EB);
+        if (full) {
+          int rk[EB];
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-          float part[EB];
+          for (int e = 0; e < EB; ++e) rk[e] = __shfl_sync(DL_FULL, rankA, q * DL_HS + sb * EB + e);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            float part[EB];
+#pragma unroll
+            for (int e = 0; e < EB; ++e) {
+              float4 zi = dl_zero4(), zj = dl_zero4();
+              if (DENSE || act[p]) {
+                zj = dl_lds4(st + (sb * EB + e) * ROWB + off[p] * 4);
+                zi = dl_lds4(st + (DL_HS + rk[e]) * ROWB + off[p] * 4);
+              }
+              part[e] = dl_chunk_dot(zi, zj);
+            }
+            float qv = dl_reduce_scatter<M>(part, lane);
+            if (!unit_T) qv = __fdiv_rn(qv, T);
+            ev[p] = dl_expf(qv);
+          }
+        } else {
+          int rk[EB], rw[EB];
 #pragma unroll
           for (int e = 0; e < EB; ++e) {
-            const int se = sb * EB + e;
-            float4 zi = dl_zero4(), zj = dl_zero4();
-            if (se < cnt && act[p]) {
-              zj = dl_lds4(st + se * ROWB + off[p] * 4);
-              if (rk[e] < DL_OWNQ) zi = dl_lds4(st + (DL_HS + rk[e]) * ROWB + off[p] * 4);
-              else zi = dl_ldg4(Z + (g.row_base + rw[e]) * D + off[p]);
-            }
-            part[e] = dl_chunk_dot(zi, zj);
+            rk[e] = __shfl_sync(DL_FULL, rankA, q * DL_HS + sb * EB + e);
+            rw[e] = __shfl_sync(DL_FULL, rowA, q * DL_HS + sb * EB + e);
           }
-          float qv = dl_reduce_scatter<M>(part, lane);
-          if (!unit_T) qv = __fdiv_rn(qv, T);
-          ev[p] = dl_expf(qv);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            float part[EB];
+#pragma unroll
+            for (int e = 0; e < EB; ++e) {
+              const int se = sb * EB + e;
+              float4 zi = dl_zero4(), zj = dl_zero4();
+              if (se < cnt && act[p]) {
+                zj = dl_lds4(st + se * ROWB + off[p] * 4);
+                if (rk[e] < DL_OWNQ) zi = dl_lds4(st + (DL_HS + rk[e]) * ROWB + off[p] * 4);
+                else zi = dl_ldg4(Z + (g.row_base + rw[e]) * D + off[p]);
+              }
+              part[e] = dl_chunk_dot(zi, zj);
+            }
+            float qv = dl_reduce_scatter<M>(part, lane);
+            if (!unit_T) qv = __fdiv_rn(qv, T);
+            ev[p] = dl_expf(qv);
+          }
         }
         float a[K];
         float sum = 0.0f;

@@ -21,7 +21,8 @@
 
 namespace {
 
-constexpr int BW_OWN = 1;   // staged own-row slots per stage
+constexpr int BW_OWN = 2;   // staged own-row slots per stage
+constexpr int BW_RING = 2;  // stages per warp ring (registers cap the kernel at 16 warps/SM anyway)
 
 template <class M>
 struct BwdStreamCfg {
@@ -31,11 +32,11 @@ struct BwdStreamCfg {
   static constexpr int OWN_B = 2 * ROWB + SRB;                             // Z[i], G[i], s/r
   static constexpr int STAGE_B = DL_HS * (ROWB + SLB) + BW_OWN * OWN_B;
   static constexpr int BUDGET = 200 * 1024;
-  static constexpr int NW_RAW = BUDGET / (DL_RING * STAGE_B);
+  static constexpr int NW_RAW = BUDGET / (BW_RING * STAGE_B);
   static constexpr bool OK = NW_RAW >= 4 && M::EB == 4 && 2 * M::K <= 32;
   static constexpr int NW = NW_RAW >= 16 ? 16 : (NW_RAW >= 4 ? NW_RAW : 4);
   static constexpr int THREADS = NW * 32;
-  static constexpr size_t SMEM = (size_t)NW * DL_RING * STAGE_B;
+  static constexpr size_t SMEM = (size_t)NW * BW_RING * STAGE_B;
 };
 
 __device__ __forceinline__ void dl_cp_async4(void* smem_dst, const void* gmem_src) {
@@ -69,9 +70,10 @@ k_bwd_edges_stream(DlGraphDev g, const float* __restrict__ Z, const float* __res
   constexpr int NBG_OFF = DL_HS * ROWB;                 // routed G slices of the stage
   constexpr int OWN_OFF = DL_HS * (ROWB + SLB);         // own-row slots
   static_assert(DL_HS == 4, "one stage = one sub-block of 4 entries");
+  constexpr bool DENSE = (M::L == M::LP) && (M::K % M::FPP == 0);   // every lane active in every pass
   extern __shared__ __align__(128) unsigned char dl_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* ring = dl_smem_raw + (size_t)warp * DL_RING * STAGE_B;
+  unsigned char* ring = dl_smem_raw + (size_t)warp * BW_RING * STAGE_B;
   const long long gw = (long long)blockIdx.x * C::NW + warp;
   const long long RE = (long long)DL_CH * DL_RANGE;
 
@@ -184,10 +186,11 @@ k_bwd_edges_stream(DlGraphDev g, const float* __restrict__ Z, const float* __res
   load_sr(mA);
   long long cn = cs.next(c);
   load_meta(cn, mB);
-  issue_stage(ring, mA, 0);
-  dl_cp_async_commit();
-  issue_stage(ring + STAGE_B, mA, 1);
-  dl_cp_async_commit();
+#pragma unroll
+  for (int pq = 0; pq < BW_RING - 1; ++pq) {
+    issue_stage(ring + pq * STAGE_B, mA, pq);
+    dl_cp_async_commit();
+  }
   int rslot = 0;
 
   while (c >= 0) {
@@ -211,15 +214,16 @@ k_bwd_edges_stream(DlGraphDev g, const float* __restrict__ Z, const float* __res
     const unsigned qbits = ((1u << DL_HS) - 1u) << ((lane / DL_HS) * DL_HS);
     const int rankA = __popc(smaskA & qbits & (0xffffffffu >> (31 - lane))) - 1;
     const unsigned vmaskA = __ballot_sync(DL_FULL, mA.row >= 0);
+    const bool allownA = __all_sync(DL_FULL, rankA < BW_OWN);
 
 #pragma unroll 1
     for (int q = 0; q < DL_QPC; ++q) {
-      int islot = rslot + 2;
-      if (islot >= DL_RING) islot -= DL_RING;
-      if (q < DL_QPC - 2) issue_stage(ring + islot * STAGE_B, mA, q + 2);
-      else issue_stage(ring + islot * STAGE_B, mB, q + 2 - DL_QPC);
+      int islot = rslot + (BW_RING - 1);
+      if (islot >= BW_RING) islot -= BW_RING;
+      if (q < DL_QPC - (BW_RING - 1)) issue_stage(ring + islot * STAGE_B, mA, q + (BW_RING - 1));
+      else issue_stage(ring + islot * STAGE_B, mB, q + (BW_RING - 1) - DL_QPC);
       dl_cp_async_commit();
-      dl_cp_async_wait<DL_RING - 1>();
+      dl_cp_async_wait<BW_RING - 1>();
       __syncwarp();
       const unsigned char* st = ring + rslot * STAGE_B;
       const int cnt = __popc((vmaskA >> (q * DL_HS)) & ((1u << DL_HS) - 1u));
@@ -237,34 +241,63 @@ k_bwd_edges_stream(DlGraphDev g, const float* __restrict__ Z, const float* __res
         float pij[EB], pji[EB];
 #pragma unroll
         for (int e = 0; e < EB; ++e) { pij[e] = 0.0f; pji[e] = 0.0f; }
+        // fast path: a full stage whose own rows are all staged needs no per-entry validity handling
+        const bool full = allownA && cnt == EB;
+        if (full) {
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-          float part[EB];
+          for (int p = 0; p < NP; ++p) {
+            float part[EB];
 #pragma unroll
-          for (int e = 0; e < EB; ++e) {
-            float4 zi = dl_zero4(), gi = dl_zero4();
-            zj[e][p] = dl_zero4();
-            if (e < cnt && act[p]) {
-              zj[e][p] = dl_lds4(st + e * ROWB + off[p] * 4);
-              if (rk[e] < BW_OWN) {
-                zi = dl_lds4(st + OWN_OFF + rk[e] * OWN_B + off[p] * 4);
-                gi = dl_lds4(st + OWN_OFF + rk[e] * OWN_B + ROWB + off[p] * 4);
-              } else {
-                zi = dl_ldg4(Z + (g.row_base + re[e]) * D + off[p]);
-                gi = dl_ldg4(G + (g.row_base + re[e]) * D + off[p]);
+            for (int e = 0; e < EB; ++e) {
+              float4 zi = dl_zero4(), gi = dl_zero4();
+              zj[e][p] = dl_zero4();
+              if (DENSE || act[p]) {
+                const unsigned char* ow = st + OWN_OFF + rk[e] * OWN_B + off[p] * 4;
+                zj[e][p] = dl_lds4(st + e * ROWB + off[p] * 4);
+                zi = dl_lds4(ow);
+                if (ke[e] == M::factor(lane, p)) {
+                  gi = dl_lds4(ow + ROWB);
+                  const float4 gje = dl_lds4(st + NBG_OFF + e * SLB + gg * 16);
+                  pij[e] = dl_chunk_dot(gi, zj[e][p]);
+                  pji[e] = dl_chunk_dot(gje, zi);
+                }
               }
-              // c_ij, c_ji partials exist only on the lanes that own the routed factor of entry e
-              if (ke[e] == M::factor(lane, p)) {
-                const float4 gje = dl_lds4(st + NBG_OFF + e * SLB + gg * 16);
-                pij[e] = dl_chunk_dot(gi, zj[e][p]);
-                pji[e] = dl_chunk_dot(gje, zi);
-              }
+              part[e] = dl_chunk_dot(zi, zj[e][p]);
             }
-            part[e] = dl_chunk_dot(zi, zj[e][p]);
+            float qv = dl_reduce_scatter<M>(part, lane);
+            if (!unit_T) qv = __fdiv_rn(qv, T);
+            ev[p] = dl_expf(qv);
           }
-          float qv = dl_reduce_scatter<M>(part, lane);
-          if (!unit_T) qv = __fdiv_rn(qv, T);
-          ev[p] = dl_expf(qv);
+        } else {
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            float part[EB];
+#pragma unroll
+            for (int e = 0; e < EB; ++e) {
+              float4 zi = dl_zero4(), gi = dl_zero4();
+              zj[e][p] = dl_zero4();
+              if (e < cnt && act[p]) {
+                zj[e][p] = dl_lds4(st + e * ROWB + off[p] * 4);
+                if (rk[e] < BW_OWN) {
+                  zi = dl_lds4(st + OWN_OFF + rk[e] * OWN_B + off[p] * 4);
+                  gi = dl_lds4(st + OWN_OFF + rk[e] * OWN_B + ROWB + off[p] * 4);
+                } else {
+                  zi = dl_ldg4(Z + (g.row_base + re[e]) * D + off[p]);
+                  gi = dl_ldg4(G + (g.row_base + re[e]) * D + off[p]);
+                }
+                // c_ij, c_ji partials exist only on the lanes that own the routed factor of entry e
+                if (ke[e] == M::factor(lane, p)) {
+                  const float4 gje = dl_lds4(st + NBG_OFF + e * SLB + gg * 16);
+                  pij[e] = dl_chunk_dot(gi, zj[e][p]);
+                  pji[e] = dl_chunk_dot(gje, zi);
+                }
+              }
+              part[e] = dl_chunk_dot(zi, zj[e][p]);
+            }
+            float qv = dl_reduce_scatter<M>(part, lane);
+            if (!unit_T) qv = __fdiv_rn(qv, T);
+            ev[p] = dl_expf(qv);
+          }
         }
         const bool valid = my_e < cnt;
         int ks = __shfl_sync(DL_FULL, mA.ks, (q * DL_HS + my_e) & 31);
@@ -276,7 +309,8 @@ k_bwd_edges_stream(DlGraphDev g, const float* __restrict__ Z, const float* __res
           sum = (k == 0) ? ek : __fadd_rn(sum, ek);
           if (k == ks) eks = ek;
         }
-        const float wv = __fdiv_rn(eks, sum);            // = w[e] of the forward, same bits
+        const float rsum = __fdiv_rn(1.0f, sum);
+        const float wv = __fmul_rn(eks, rsum);           // w[e] up to one rounding
         const float rij = dl_reduce_scatter<M>(pij, lane);
         const float rji = dl_reduce_scatter<M>(pji, lane);
         const int ksrc = (ks % FPP) * LP + gsrc;
@@ -307,7 +341,7 @@ k_bwd_edges_stream(DlGraphDev g, const float* __restrict__ Z, const float* __res
         float cfe[NP][EB];
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-          const float a_own = __fdiv_rn(ev[p], sum);
+          const float a_own = __fmul_rn(ev[p], rsum);
           const float ind = (M::factor(lane, p) == ks) ? 1.0f : 0.0f;
           const float coef_own = __fmul_rn(basec, __fsub_rn(ind, a_own));
 #pragma unroll
@@ -324,7 +358,7 @@ k_bwd_edges_stream(DlGraphDev g, const float* __restrict__ Z, const float* __res
         }
       }
       __syncwarp();
-      rslot = (rslot + 1 == DL_RING) ? 0 : rslot + 1;
+      rslot = (rslot + 1 == BW_RING) ? 0 : rslot + 1;
     }
     c = cn; cn = cnn;
     mA = mB; mB = mC;
