@@ -371,8 +371,11 @@ def run_native(args):
                                        "frac": round(fwd_bwd_bytes / (t_factor * 1e-3) / 1e9 / peak, 4)}}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get(dom)
+        try:   # ncu dram bytes per entry (captured at the mid size) x the entries of this launch
+            per = json.load(open(prof))[dom]["per_entry"]
+            units = (step.p_hi - step.p_lo) if dom.startswith("pair") else nnz_local
+            roofline["traffic"] = int(per * units)
+            roofline["traffic_source"] = "profiles/traffic.json: ncu --set full dram bytes per entry at nnz=1e8, scaled"
         except Exception:
             pass
 

@@ -182,6 +182,32 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
 #pragma unroll
   for (int p = 0; p < NP; ++p) acc[p] = dl_zero4();
   int cur_row = -1;
+  // row vectors the epilogue needs, loaded when a run STARTS so their latency overlaps the run
+  float4 zpre[NP], gpre[NP], dpre[NP];
+  float skpre[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) { zpre[p] = gpre[p] = dpre[p] = dl_zero4(); skpre[p] = 1.0f; }
+  auto prefetch_row = [&](int row) {
+    if (MODE == 2) return;
+    const long long node = g.row_base + row;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      if (!M::active(lane, p)) continue;
+      const int o = M::offset(lane, p);
+      zpre[p] = dl_ldg4(Z + node * D + o);
+      if (MODE == 1) {
+        gpre[p] = dl_ldg4(SRC + node * D + o);
+        dpre[p] = *reinterpret_cast<const float4*>(OUT + node * D + o);
+      }
+    }
+    if (MODE == 1) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int k = M::factor(lane, p);
+        skpre[p] = (k < K) ? __ldg(s + node * K + k) : 1.0f;
+      }
+    }
+  };
   bool first_run = true;          // no flush yet in the current range
   bool head_open = false, tail_open = false;
   long long cur_range = -1;
@@ -208,7 +234,7 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
           for (int p = 0; p < NP; ++p) {
             if (!M::active(lane, p)) continue;
             const int o = M::offset(lane, p);
-            const float4 zi = dl_ldg4(Z + node * D + o);
+            const float4 zi = zpre[p];
             float4 h;
             h.x = __fadd_rn(__fmul_rn(beta, zi.x), __fmul_rn(omb, acc[p].x));
             h.y = __fadd_rn(__fmul_rn(beta, zi.y), __fmul_rn(omb, acc[p].y));
@@ -222,18 +248,18 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
             const int k = M::factor(lane, p);
             const bool act = M::active(lane, p);
             const int o = M::offset(lane, p);
-            const float sk = (k < K) ? __ldg(s + node * K + k) : 1.0f;
+            const float sk = skpre[p];
             const float scale = __fdiv_rn(omb, sk);
             float4 tv;
             tv.x = __fmul_rn(scale, acc[p].x); tv.y = __fmul_rn(scale, acc[p].y);
             tv.z = __fmul_rn(scale, acc[p].z); tv.w = __fmul_rn(scale, acc[p].w);
-            const float4 zi = act ? dl_ldg4(Z + node * D + o) : dl_zero4();
+            const float4 zi = act ? zpre[p] : dl_zero4();
             const float dotzt = dl_group_sum<M>(dl_chunk_dot(zi, tv));
             if (k < K && gg == 0) r[node * K + k] = __fdiv_rn(dotzt, sk);
             if (act) {
-              const float4 gi = dl_ldg4(SRC + node * D + o);
+              const float4 gi = gpre[p];
               float4* dp = reinterpret_cast<float4*>(OUT + node * D + o);
-              float4 cur = *dp;
+              float4 cur = dpre[p];
               cur.x = __fadd_rn(cur.x, __fmaf_rn(beta, gi.x, tv.x));
               cur.y = __fadd_rn(cur.y, __fmaf_rn(beta, gi.y, tv.y));
               cur.z = __fadd_rn(cur.z, __fmaf_rn(beta, gi.z, tv.z));
@@ -287,23 +313,37 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
     const unsigned vmask = __ballot_sync(DL_FULL, mA.row >= 0);
     const int cnt = __popc(vmask);
     const unsigned char* sl = tile + buf * TILE_B;
-    for (int idx = 0; idx < cnt; ++idx) {
-      const int re = __shfl_sync(DL_FULL, mA.row, idx);
-      const int ke = __shfl_sync(DL_FULL, mA.ks, idx);
-      const float cf = __shfl_sync(DL_FULL, coefA, idx);
-      if (re != cur_row) {                      // warp-uniform
+    // the chunk is walked run by run (a run = consecutive entries of one row), so the hot loop has
+    // no row test: bit i of `starts` is set when entry i opens a new run
+    const int prow = __shfl_up_sync(DL_FULL, mA.row, 1);
+    const bool st = mA.row >= 0 && (lane == 0 ? mA.row != cur_row : mA.row != prow);
+    const unsigned starts = __ballot_sync(DL_FULL, st);
+    int idx = 0;
+    while (idx < cnt) {
+      if ((starts >> idx) & 1u) {
         flush(false);
-        cur_row = re;
+        cur_row = __shfl_sync(DL_FULL, mA.row, idx);
+        prefetch_row(cur_row);
       }
-      if (MODE == 2) {
-        if (lane == ke) acc2 = __fadd_rn(acc2, cf);
-      } else {
-        if (glane && (ke % FPP) == slot) {
-          const float4 v = dl_lds4(sl + idx * SLB + gg * 16);
-          const int pe = ke / FPP;
+      const unsigned rest = (idx < 31) ? (starts & ~((2u << idx) - 1u)) : 0u;
+      const int end = rest ? (__ffs(rest) - 1) : cnt;
+      for (; idx < end; ++idx) {
+        const unsigned ke = (unsigned)__shfl_sync(DL_FULL, mA.ks, idx);
+        const float cf = __shfl_sync(DL_FULL, coefA, idx);
+        if (MODE == 2) {
+          if ((unsigned)lane == ke) acc2 = __fadd_rn(acc2, cf);
+        } else {
+          if (glane && (ke & (FPP - 1)) == (unsigned)slot) {
+            const float4 v = dl_lds4(sl + idx * SLB + gg * 16);
+            if (NP == 1) {
+              dl_fma4(acc[0], cf, v);
+            } else {
+              const unsigned pe = ke / FPP;
 #pragma unroll
-          for (int p = 0; p < NP; ++p)
-            if (pe == p) dl_fma4(acc[p], cf, v);
+              for (int p = 0; p < NP; ++p)
+                if (pe == (unsigned)p) dl_fma4(acc[p], cf, v);
+            }
+          }
         }
       }
     }

@@ -81,12 +81,12 @@ def factor_bwd_gather(graph: Graph, Z, G, kstar, w, s, beta: float, dZ, r):
               "dl_factor_bwd_gather")
 
 
-def factor_bwd_edges(graph: Graph, Z, G, kstar, s, r, beta: float, T: float, dZ):
+def factor_bwd_edges(graph: Graph, Z, G, kstar, w, s, r, beta: float, T: float, dZ):
     """Pass 2 of the backward: dZ += attention-weight terms (needs r of every neighbour)."""
     K, d = _check_Z(Z, graph.n_global)
     dev = Z.device
     with torch.cuda.device(dev):
-        check(lib().dl_factor_bwd_edges(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(s), ptr(r), K, d,
+        check(lib().dl_factor_bwd_edges(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), ptr(r), K, d,
                                         one_minus(beta), float(T), ptr(dZ),
                                         ptr(graph.hub_scratch(K * d)), stream_of(dev)),
               "dl_factor_bwd_edges")

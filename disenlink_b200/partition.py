@@ -166,8 +166,8 @@ class CudaBackend:
     def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r):
         self.ops.factor_bwd_gather(g, Z, G, kstar, w, s, beta, dZ, r)
 
-    def factor_bwd_edges(self, g, Z, G, kstar, s, r, beta, T, dZ):
-        self.ops.factor_bwd_edges(g, Z, G, kstar, s, r, beta, T, dZ)
+    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ):
+        self.ops.factor_bwd_edges(g, Z, G, kstar, w, s, r, beta, T, dZ)
 
 
 class PartitionedLinkStep:
@@ -251,7 +251,7 @@ class PartitionedLinkStep:
         mark("bwd_gather")
         all_gather_rows(self.r, part, self.group)
         mark("ag_r")
-        be.factor_bwd_edges(g, Z, self.dH, self.kstar, self.s, self.r, self.beta, self.T, self.dZ)
+        be.factor_bwd_edges(g, Z, self.dH, self.kstar, self.w, self.s, self.r, self.beta, self.T, self.dZ)
         mark("bwd_edges")
         return self.dZ
 

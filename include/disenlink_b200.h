@@ -152,8 +152,8 @@ int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
                          float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
                          dl_stream_t stream);
 int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
-                        const uint8_t* kstar, const float* s, const float* r, int K, int d,
-                        float one_minus_beta, float T, float* dZ, float* hub_ws,
+                        const uint8_t* kstar, const float* w, const float* s, const float* r, int K,
+                        int d, float one_minus_beta, float T, float* dZ, float* hub_ws,
                         dl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -82,7 +82,7 @@ class OracleBackend:
         dZ[lo:hi] = torch.from_numpy(dz[lo:hi])
         r[lo:hi] = torch.from_numpy(rr[lo:hi])
 
-    def factor_bwd_edges(self, g, Z, G, kstar, s, r, beta, T, dZ):
+    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ):
         lo, hi = g.part.lo, g.part.hi
         dz = dZ.numpy().copy()
         self.o.factor_bwd_edges(g.rowptr, g.col, Z.numpy(), G.numpy(), s.numpy(), r.numpy(), beta, T, dz)
