@@ -354,8 +354,9 @@ def run_native(args):
     ab["pair_bwd"] = int(step.inc.nnz) * (8 * D + 12) + part.n_local * 16 * D
     # kernels of libdisenlink_b200.so per step (streaming path): attention = routing + row sums +
     # chain + empty rows (4); aggregation = gather + chain + empty rows (3); pair scoring fwd (1);
-    # decoder backward (1, +1 hub fix-up); backward pass 1 (3); backward pass 2 = stream + chain (2)
-    launches_per_step = 14 + (1 if step.inc.n_hub > 0 else 0)
+    # decoder backward = stream + chain + empty nodes (3); backward pass 1 (3); backward pass 2 =
+    # stream + chain (2)
+    launches_per_step = 16
     kernels = {}
     for kname in KERNEL_PHASES:
         ms = phase_ms[kname]

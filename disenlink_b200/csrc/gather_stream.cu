@@ -30,7 +30,9 @@ namespace {
 constexpr int GS_WARPS = 16;   // warps per CTA
 
 // flat width of a row's accumulator / carry record
-__host__ __device__ constexpr int carry_width(int mode, int K, int d) { return mode == 2 ? K : K * d; }
+__host__ __device__ constexpr int carry_width(int mode, int K, int d) {
+  return mode == 2 ? K : (mode == 4 ? 2 * K * d : K * d);
+}
 
 // ---- row epilogues on a flat accumulator held by one thread-strided warp (rare rows) ----------
 __device__ __forceinline__ void epilogue_flat(int mode, int lane, long long node, int K, int d,
@@ -39,7 +41,12 @@ __device__ __forceinline__ void epilogue_flat(int mode, int lane, long long node
                                               const float* __restrict__ s, float beta, float omb,
                                               float* __restrict__ OUT, float* __restrict__ r) {
   const long long D = (long long)K * d;
-  if (mode == 3) {                       // plain accumulate (backward pass 2 partial sums)
+  if (mode == 4) {                       // decoder backward: record = [dZ row | dH row], overwrite
+    for (long long x = lane; x < D; x += 32) {
+      OUT[node * D + x] = acc ? acc[x] : 0.0f;
+      r[node * D + x] = acc ? acc[D + x] : 0.0f;
+    }
+  } else if (mode == 3) {                // plain accumulate (backward pass 2 partial sums)
     if (acc)
       for (long long x = lane; x < D; x += 32) OUT[node * D + x] = __fadd_rn(OUT[node * D + x], acc[x]);
   } else if (mode == 2) {
@@ -436,6 +443,21 @@ int dl_gather_chain_add(const DlGraphDev& g, int K, int d, float* scratch, float
   const int W = K * d;
   k_gather_chain<<<small_grid(n_ranges), DL_CTA, 0, st>>>(g, 3, K, d, scratch, nullptr, nullptr, nullptr, 0.0f,
                                                           0.0f, OUT, nullptr, scratch + (size_t)n_ranges * 2 * W);
+  DL_LAUNCH_CHECK();
+  return DL_OK;
+}
+
+// chain fix-up + empty nodes for the streaming decoder backward (mode 4: OUT = dZ, second = dH)
+int dl_gather_chain_pair(const DlGraphDev& g, int K, int d, float* scratch, float* dZ, float* dH,
+                         cudaStream_t st) {
+  const long long RE = (long long)DL_CH * DL_RANGE;
+  const long long n_ranges = (g.nnz + RE - 1) / RE;
+  const int W = 2 * K * d;
+  k_gather_chain<<<small_grid(n_ranges), DL_CTA, 0, st>>>(g, 4, K, d, scratch, nullptr, nullptr, nullptr, 0.0f,
+                                                          0.0f, dZ, dH, scratch + (size_t)n_ranges * 2 * W);
+  DL_LAUNCH_CHECK();
+  k_gather_empty_rows<<<small_grid((g.N + 31) / 32), DL_CTA, 0, st>>>(g, 4, K, d, nullptr, nullptr, nullptr,
+                                                                     0.0f, 0.0f, dZ, dH);
   DL_LAUNCH_CHECK();
   return DL_OK;
 }

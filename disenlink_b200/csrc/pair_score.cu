@@ -10,6 +10,8 @@
 //
 // HBM bytes per pair (D=128): forward 8 (ids) + 4*512 + 4; backward 2 * (4 + 4 + 4 + 2*512) per
 // pair (each pair is visited from both endpoints) + per node 2*512 in, 2*512 out.
+#include <stdlib.h>
+
 #include "dl_dispatch.cuh"
 
 namespace {
@@ -318,6 +320,10 @@ int dl_pair_score_bwd(const dl_graph* inc_host, const int32_t* inc_pair, const f
   const DlGraphDev g = dl_graph_dev(inc_host);
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
+  if (!getenv("DL_NO_STREAM"))
+    rc = dl_launch_pair_bwd_stream(g, inc_pair, Z, H, dS, K, d, T, dZ, dH, hub_ws, st);
+  if (rc == DL_OK) return DL_OK;
+  if (rc != -1000) return rc;
 #define BODY_MACRO(M) rc = launch_pair_bwd<M>(g, n_items, inc_pair, Z, H, dS, T, dZ, dH, hub_ws, st);
   DL_DISPATCH_SHAPES()
 #undef BODY_MACRO
