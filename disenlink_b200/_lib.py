@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdisenlink_b200.so")
+# DL_LIB_PATH: load another build of the same library (A/B experiments with kernel variants)
+LIB_PATH = os.environ.get("DL_LIB_PATH") or os.path.join(_HERE, "libdisenlink_b200.so")
 
 DL_MAX_K = 32
 DL_MAX_D = 256

@@ -141,9 +141,9 @@ struct DlRowIter {
 
 // ---- canonical exp ------------------------------------------------------------------------
 __device__ __forceinline__ float dl_expf(float x) {
-  if (x != x) return x;
-  x = fminf(x, 89.0f);
-  x = fmaxf(x, -104.0f);
+  // clamps written as selects so that a NaN argument flows through to a NaN result without a branch
+  x = (x > 89.0f) ? 89.0f : x;
+  x = (x < -104.0f) ? -104.0f : x;
   float t = __fmul_rn(x, 1.44269504088896341f);
   float n = rintf(t);
   float r = __fmaf_rn(n, -0.693359375f, x);

@@ -128,3 +128,8 @@ int dl_gather_chain_pair(const DlGraphDev& g, int K, int d, float* scratch, floa
 int dl_launch_pair_bwd_stream(const DlGraphDev& g, const int* inc_pair, const float* Z, const float* H,
                               const float* dS, int K, int d, float T, float* dZ, float* dH, float* scratch,
                               cudaStream_t st);
+
+// Factor-per-lane backward pass 2 (bwd_fl.cu).  Returns -1000 when (K, d) has no instantiation.
+int dl_launch_bwd_edges_fl(const DlGraphDev& g, const float* Z, const float* G, const unsigned char* kstar,
+                           const float* s, const float* r, int K, int d, float omb, float T, float* dZ,
+                           float* scratch, cudaStream_t st);

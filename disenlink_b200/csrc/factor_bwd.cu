@@ -442,6 +442,11 @@ int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
     rc = dl_launch_bwd_edges_split(g, Z, G, kstar, w, s, r, K, d, one_minus_beta, T, dZ, hub_ws, st);
   if (rc == DL_OK) return DL_OK;
   if (rc != -1000) return rc;
+  // factor-per-lane kernel (bwd_fl.cu) for the K <= 8, d <= 16 shape class; DL_NO_FL=1 disables it
+  if (!getenv("DL_NO_STREAM") && !getenv("DL_NO_FL"))
+    rc = dl_launch_bwd_edges_fl(g, Z, G, kstar, s, r, K, d, one_minus_beta, T, dZ, hub_ws, st);
+  if (rc == DL_OK) return DL_OK;
+  if (rc != -1000) return rc;
   if (!getenv("DL_NO_STREAM"))
     rc = dl_launch_bwd_edges_stream(g, Z, G, kstar, s, r, K, d, one_minus_beta, T, dZ, hub_ws, st);
   if (rc == DL_OK) return DL_OK;
