@@ -80,6 +80,10 @@ __device__ __forceinline__ float fl_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(x));
   return v;
 }
+__device__ __forceinline__ void fl_red_add4(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void fl_cp16(unsigned dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -235,14 +239,13 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
 #pragma unroll
           for (int c = 0; c < C4; ++c) *reinterpret_cast<float4*>(dst + c * 4) = dz[c];
         } else {
+          // dZ[i] += row sum.  This warp is the only writer of the row in this kernel (rows cut by a
+          // range boundary go through the carries), so a fire-and-forget vector reduction gives the
+          // same value as load-add-store in any schedule -- without stalling on the load.  (f32
+          // reductions flush subnormals to zero.)
           float* dst = dZ + (g.row_base + cur_row) * D + kap * d;
 #pragma unroll
-          for (int c = 0; c < C4; ++c) {
-            float4 cur = *reinterpret_cast<float4*>(dst + c * 4);
-            cur.x = __fadd_rn(cur.x, dz[c].x); cur.y = __fadd_rn(cur.y, dz[c].y);
-            cur.z = __fadd_rn(cur.z, dz[c].z); cur.w = __fadd_rn(cur.w, dz[c].w);
-            *reinterpret_cast<float4*>(dst + c * 4) = cur;
-          }
+          for (int c = 0; c < C4; ++c) fl_red_add4(dst + c * 4, dz[c]);
         }
       }
       first_run = false;
