@@ -1,0 +1,40 @@
+"""profiles/traffic.json from an ncu summary written by tools/ncu_summary.py.
+Usage: python tools/make_traffic_json.py profiles/r01_ncu_full_mid.txt NNZ P > profiles/traffic.json"""
+import json
+import re
+import sys
+
+
+def main(path, nnz, pairs):
+    kernels, cur = {}, None
+    for line in open(path):
+        m = re.match(r"----- void <unnamed>::(.*)", line)
+        if m:
+            cur = kernels.setdefault(m.group(1).strip(), {})
+            continue
+        m = re.match(r"\s+(\S+)\s+([\d.]+) (\S+)", line)
+        if m and cur is not None:
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(m.group(3), 1.0)
+            if m.group(1) == "dram__bytes_read.sum":
+                cur["dram_bytes_read"] = float(m.group(2)) * scale
+            elif m.group(1) == "dram__bytes_write.sum":
+                cur["dram_bytes_write"] = float(m.group(2)) * scale
+            elif m.group(1) == "gpu__time_duration.sum":
+                cur["duration_ms_under_ncu"] = float(m.group(2))
+    for k in kernels.values():
+        k["traffic"] = k.get("dram_bytes_read", 0.0) + k.get("dram_bytes_write", 0.0)
+    phase_of = [("bwd_edges", "k_bwd_edges", nnz), ("attn_fwd", "k_attn_stream", nnz),
+                ("spmm_fwd", "k_gather_stream<DlMap<8, 16>, 0>", nnz),
+                ("bwd_gather", "k_gather_stream<DlMap<8, 16>, 1>", nnz),
+                ("pair_fwd", "k_pair_score_fwd", pairs), ("pair_bwd", "k_pair_bwd_stream", pairs)]
+    out = {"workload": f"mid (nnz={nnz}, K=8, d=16, P={pairs}) -- ncu --set full is too slow at c5; bytes scale "
+                       "with nnz / P", "source": path, "nnz": nnz, "pairs": pairs, "kernels": kernels}
+    for phase, pat, units in phase_of:
+        for name, k in kernels.items():
+            if name.startswith(pat):
+                out[phase] = {"kernel": name, "traffic_bytes_per_launch": k["traffic"], "per_entry": k["traffic"] / units}
+    json.dump(out, sys.stdout, indent=1)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]))
