@@ -355,8 +355,8 @@ def run_native(args):
     # kernels of libdisenlink_b200.so per step (streaming path): attention = routing + row sums +
     # chain + empty rows (4); aggregation = gather + chain + empty rows (3); pair scoring fwd (1);
     # decoder backward = stream + chain + empty nodes (3); backward pass 1 (3); backward pass 2 =
-    # stream + chain (2)
-    launches_per_step = 16
+    # stream + chain (2); weighted BCE forward+backward (2)
+    launches_per_step = 18
     kernels = {}
     for kname in KERNEL_PHASES:
         ms = phase_ms[kname]

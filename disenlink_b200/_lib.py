@@ -65,6 +65,8 @@ SIGNATURES = {
     "dl_allpairs_score_bwd": (_int, [_vp, _vp, _vp, _i64, _int, _int, _f, _vp, _vp, _vp]),
     "dl_dense_alpha0": (_int, [_vp, _i64, _int, _int, _f, _vp, _vp]),
     "dl_dense_att": (_int, [_GP, _vp, _vp, _vp, _int, _vp, _vp]),
+    "dl_link_bce_workspace_bytes": (_i64, []),
+    "dl_link_bce": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
 }
 
 _lib = None

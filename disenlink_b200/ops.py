@@ -246,6 +246,29 @@ def pair_score(Z, H, batch: PairBatch, T: float = 1.0, as_prob: bool = True):
     return _PairScore.apply(Z, H, batch, T, as_prob)
 
 
+def link_bce(prob, labels, weights=None, want_grad: bool = True, dS=None):
+    """sum_p weights[p] * BCE(prob[p], labels[p]) and dL/dlogit in one pass (dl_link_bce).
+    -> (loss 0-dim f32 tensor, dS [P] or None).  [ref: main_disentangled.py:195]"""
+    dev = prob.device
+    require_cuda(prob, "prob")
+    P = int(prob.numel())
+    prob = prob.contiguous()
+    labels = labels.to(torch.float32).contiguous()
+    if weights is not None:
+        weights = weights.to(torch.float32).contiguous()
+    L = lib()
+    with torch.cuda.device(dev):
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        if want_grad and dS is None:
+            dS = torch.empty(P, dtype=torch.float32, device=dev)
+        ws_bytes = int(L.dl_link_bce_workspace_bytes())
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(L.dl_link_bce(ptr(prob), ptr(labels), ptr(weights) if weights is not None else None, P,
+                            ptr(dS) if want_grad else None, ptr(loss), ptr(ws), ws_bytes, stream_of(dev)),
+              "dl_link_bce")
+    return loss, (dS if want_grad else None)
+
+
 class _LinkBCELoss(torch.autograd.Function):
     """Whole hot path as one differentiable op with explicit buffer reuse (4 [N,K,d] buffers live):
     attention -> aggregation -> pair scores -> weighted BCE -> decoder backward -> factor backward.
@@ -257,20 +280,16 @@ class _LinkBCELoss(torch.autograd.Function):
         kstar, w, s = edge_attn_fwd(graph, Zc, T)
         H = factor_spmm_fwd(graph, Zc, kstar, w, s, beta)
         _, prob = pair_score_fwd(Zc, H, batch, T, want_logit=False)
-        with torch.enable_grad():
-            p = prob.detach().requires_grad_(True)
-            # torch's own BCE (log clamped at -100, backward clamped at 1e-12) keeps the script's
-            # numerics; weights fold the means and the 1/m of main_disentangled.py:195
-            loss = (torch.nn.functional.binary_cross_entropy(p, labels, reduction="none") * weights).sum()
-            need_grad = ctx.needs_input_grad[0]
-            dprob = torch.autograd.grad(loss, p)[0] if need_grad else None
+        need_grad = ctx.needs_input_grad[0]
+        # torch's BCE numerics (log clamped at -100, backward clamped at 1e-12) in one fused pass;
+        # weights fold the means and the 1/m of main_disentangled.py:195
+        loss, dS = link_bce(prob, labels, weights, want_grad=need_grad)
         if need_grad:
-            dS = dprob * (1.0 - prob) * prob
             dZ, dH = pair_score_bwd(Zc, H, batch, dS, T)
             factor_bwd(graph, Zc, dH, kstar, w, s, beta, T, dZ=dZ)
             ctx.save_for_backward(dZ)
         ctx.mark_non_differentiable(prob, H)
-        return loss.detach(), prob, H
+        return loss, prob, H
 
     @staticmethod
     def backward(ctx, gloss, _gp, _gh):

@@ -163,6 +163,11 @@ class CudaBackend:
                                           ptr(dZ), ptr(dH), ptr(inc.hub_scratch(2 * K * d)),
                                           stream_of(dev)), "dl_pair_score_bwd")
 
+    def link_bce(self, prob, labels, weights, dS):
+        """-> loss (0-dim tensor); dS [P] written in place."""
+        loss, _ = self.ops.link_bce(prob, labels, weights, want_grad=True, dS=dS)
+        return loss
+
     def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r):
         self.ops.factor_bwd_gather(g, Z, G, kstar, w, s, beta, dZ, r)
 
@@ -231,13 +236,8 @@ class PartitionedLinkStep:
 
     def loss_and_grad_logit(self):
         """weighted BCE over all pairs and dL/dlogit (every rank evaluates the full P-vector; it
-        is P floats).  d/dlogit of BCE(sigmoid(S), y) = (p - y)."""
-        p = self.prob
-        # F.binary_cross_entropy semantics: log terms clamped at -100
-        self.loss = -(self.weights * (self.labels * torch.log(p).clamp_min(-100.0) +
-                                      (1 - self.labels) * torch.log(1 - p).clamp_min(-100.0))).sum()
-        torch.sub(p, self.labels, out=self.dS)
-        self.dS.mul_(self.weights)
+        is P floats), with F.binary_cross_entropy's clamps (see dl_link_bce)."""
+        self.loss = self.be.link_bce(self.prob, self.labels, self.weights, self.dS)
         self.mark("loss")
         return self.loss
 

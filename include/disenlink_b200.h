@@ -204,6 +204,17 @@ int dl_dense_alpha0(const float* Z, int64_t N, int K, int d, float T, float* alp
 int dl_dense_att(const dl_graph* g_host, const uint8_t* kstar, const float* w, const float* s,
                  int K, float* att, dl_stream_t stream);
 
+/* ---- weighted BCE over a pair list, forward + backward fused ------------------------------
+ * [ref: main_disentangled.py:195 -- F.binary_cross_entropy(a_pred[mask == 1], target) summed over the
+ * positive mask and the m negative masks; the per-pair weights fold the means and the 1/m.]
+ *   loss[0] = sum_p weights[p] * -( y log p + (1 - y) log(1 - p) ),  logs clamped at -100 (torch)
+ *   dS[p]   = weights[p] (p - y) / max(p (1 - p), 1e-12) * (1 - p) p      (dL/dlogit; NULL: skipped)
+ * weights may be NULL (all ones).  ws: >= dl_link_bce_workspace_bytes() bytes of device scratch.
+ * Deterministic: partial sums are combined in a fixed order. */
+int64_t dl_link_bce_workspace_bytes(void);
+int dl_link_bce(const float* prob, const float* labels, const float* weights, int64_t P, float* dS,
+                float* loss, void* ws, int64_t ws_bytes, dl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

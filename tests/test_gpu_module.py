@@ -125,3 +125,36 @@ def test_link_bce_loss_matches_script_semantics():
     assert abs(loss.item() - float(g["ref_loss"])) < TOL * abs(float(g["ref_loss"]))
     assert relerr(Z.grad.cpu().numpy(), g["ref_dZ"]) < 5 * TOL
     assert relerr(H.cpu().numpy().reshape(n, -1), g["ref_H"]) < TOL
+
+
+@pytest.mark.parametrize("P", [0, 1, 1000, 1 << 20])
+def test_link_bce_kernel_vs_oracle_and_torch(P):
+    """dl_link_bce == oracle.bce_weighted == torch's own F.binary_cross_entropy + autograd through a
+    sigmoid, including saturated scores (p == 0 or 1 exactly: clamped log, zero gradient)."""
+    from disenlink_b200 import ops
+    from oracle import oracle
+    rng = np.random.default_rng(P)
+    logit = (rng.standard_normal(P) * 6).astype(np.float32)
+    if P >= 1000:
+        logit[:8] = [200, -200, 120, -120, 17, -17, 0, 40]          # exact 1 / 0 after sigmoid in fp32
+    y = (rng.random(P) < 0.3).astype(np.float32)
+    w = rng.random(P).astype(np.float32) / max(P, 1)
+    S = torch.from_numpy(logit).to(DEV).requires_grad_(True)
+    prob = torch.sigmoid(S)
+    yt, wt = torch.from_numpy(y).to(DEV), torch.from_numpy(w).to(DEV)
+    loss, dS = ops.link_bce(prob.detach(), yt, wt)
+    want_loss, want_dS = oracle.bce_weighted(prob.detach().cpu().numpy(), y, w)
+    assert abs(loss.item() - want_loss) <= 1e-6 * max(abs(want_loss), 1e-30) + 1e-12
+    if P:
+        assert np.abs(dS.cpu().numpy() - want_dS).max() <= 1e-6 * max(np.abs(want_dS).max(), 1e-30)
+        ref = (F.binary_cross_entropy(prob, yt, reduction="none") * wt).sum()
+        ref.backward()
+        assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+        assert np.abs(dS.cpu().numpy() - S.grad.cpu().numpy()).max() <= 1e-6 * float(S.grad.abs().max())
+        # unweighted variant (weights = NULL) and loss-only variant
+        l1, none = ops.link_bce(prob.detach(), yt, None, want_grad=False)
+        assert none is None
+        assert abs(l1.item() - oracle.bce_weighted(prob.detach().cpu().numpy(), y)[0]) <= 1e-6 * abs(l1.item())
+        # bitwise run-to-run determinism of the reduction
+        l2, _ = ops.link_bce(prob.detach(), yt, wt)
+        assert l2.item() == loss.item()

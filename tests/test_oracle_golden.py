@@ -151,3 +151,22 @@ def test_dot_is_symmetric_and_accurate(oracle):
         a, b = oracle.dot(x, y), oracle.dot(y, x)
         assert a.view(np.uint32) == b.view(np.uint32)
         assert abs(float(a) - float(np.dot(x.astype(np.float64), y.astype(np.float64)))) < 1e-5 * d
+
+
+def test_bce_weighted_matches_torch(oracle):
+    """oracle.bce_weighted against torch's own BCE + autograd through a sigmoid (CPU), saturated
+    scores included.  [ref: main_disentangled.py:195]"""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(5)
+    logit = (rng.standard_normal(4096) * 6).astype(np.float32)
+    logit[:6] = [200, -200, 120, -120, 17, -17]
+    y = (rng.random(4096) < 0.3).astype(np.float32)
+    w = rng.random(4096).astype(np.float32)
+    S = torch.from_numpy(logit).requires_grad_(True)
+    p = torch.sigmoid(S)
+    ref = (F.binary_cross_entropy(p, torch.from_numpy(y), reduction="none") * torch.from_numpy(w)).sum()
+    ref.backward()
+    loss, dS = oracle.bce_weighted(p.detach().numpy(), y, w)
+    assert abs(loss - ref.item()) <= 2e-6 * abs(ref.item())
+    assert np.abs(dS - S.grad.numpy()).max() <= 1e-6 * float(S.grad.abs().max())

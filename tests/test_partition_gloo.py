@@ -74,6 +74,11 @@ class OracleBackend:
         dZ[lo:hi] = torch.from_numpy(a[lo:hi])
         dH[lo:hi] = torch.from_numpy(b[lo:hi])
 
+    def link_bce(self, prob, labels, weights, dS):
+        loss, ds = self.o.bce_weighted(prob.numpy(), labels.numpy(), weights.numpy())
+        dS.copy_(torch.from_numpy(ds))
+        return torch.tensor(loss, dtype=torch.float32)
+
     def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r):
         lo, hi = g.part.lo, g.part.hi
         dz, rr = dZ.numpy().copy(), np.zeros(tuple(r.shape), np.float32)
