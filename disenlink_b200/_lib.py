@@ -67,6 +67,9 @@ SIGNATURES = {
     "dl_dense_att": (_int, [_GP, _vp, _vp, _vp, _int, _vp, _vp]),
     "dl_link_bce_workspace_bytes": (_i64, []),
     "dl_link_bce": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "dl_roc_auc_workspace_bytes": (_i64, [_i64]),
+    "dl_roc_auc": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "dl_structured_negative_sampling": (_int, [_GP, _vp, _i64, _i64, _c.c_uint64, _int, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -43,8 +43,10 @@ class Graph:
 
     # ------------------------------------------------------------------ constructors
     @classmethod
-    def from_edges(cls, src: torch.Tensor, dst: torch.Tensor, n_nodes: int) -> "Graph":
+    def from_edges(cls, src: torch.Tensor, dst: torch.Tensor, n_nodes: int, symmetrize: bool = True) -> "Graph":
         """Symmetrise + de-duplicate directed edge columns (self-loops kept).
+        ``symmetrize=False`` keeps the directed columns as they are (de-duplicated) -- the edge set
+        structured negative sampling tests membership against.
 
         [ref: main_disentangled.py:137-142]"""
         require_cuda(src, "src")
@@ -60,9 +62,14 @@ class Graph:
             meta = torch.zeros(2, dtype=torch.int64, device=dev)  # [nnz, status(int32 in low word)]
             ws_bytes = L.dl_csr_build_workspace_bytes(E, N)
             ws = _ws(ws_bytes, dev)
-            check(L.dl_csr_build(ptr(src), ptr(dst), E, N, ptr(rowptr), ptr(col), ptr(meta),
-                                 meta[1:].data_ptr(), ptr(ws), ws_bytes, stream_of(dev)),
-                  "dl_csr_build")
+            if symmetrize:
+                check(L.dl_csr_build(ptr(src), ptr(dst), E, N, ptr(rowptr), ptr(col), ptr(meta),
+                                     meta[1:].data_ptr(), ptr(ws), ws_bytes, stream_of(dev)),
+                      "dl_csr_build")
+            else:
+                check(L.dl_csr_build_rect(ptr(src), ptr(dst), E, N, N, 0, ptr(rowptr), ptr(col), ptr(meta),
+                                          meta[1:].data_ptr(), ptr(ws), ws_bytes, stream_of(dev)),
+                      "dl_csr_build_rect")
             nnz, status = (int(x) for x in meta.cpu())
             status = ctypes.c_int32(status & 0xFFFFFFFF).value
             if status != 0:

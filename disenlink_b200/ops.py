@@ -269,6 +269,64 @@ def link_bce(prob, labels, weights=None, want_grad: bool = True, dS=None):
     return loss, (dS if want_grad else None)
 
 
+def structured_negative_sampling(edge_index, num_nodes=None, seed: int = 0, graph: Graph = None,
+                                 max_tries: int = 64):
+    """torch_geometric.utils.structured_negative_sampling on the device: for every edge column
+    (i, j) a node k with (i, k) not an edge column.  -> (i, j, k) int64 tensors [E].
+    Seedable (counter-based Philox, see dl_structured_negative_sampling); `graph` = optional cached
+    directed CSR of edge_index (Graph.from_edges(..., symmetrize=False)).
+    [ref: main_disentangled.py:160]"""
+    require_cuda(edge_index, "edge_index")
+    dev = edge_index.device
+    i = edge_index[0].to(torch.int64).contiguous()
+    j = edge_index[1].to(torch.int64).contiguous()
+    E = int(i.numel())
+    if num_nodes is None:
+        num_nodes = int(edge_index.max().item()) + 1 if E else 0
+    N = int(num_nodes)
+    if graph is None:
+        graph = Graph.from_edges(i, j, N, symmetrize=False)
+    with torch.cuda.device(dev):
+        k = torch.empty(E, dtype=torch.int64, device=dev)
+        failed = torch.zeros(1, dtype=torch.int32, device=dev)
+        if E:
+            check(lib().dl_structured_negative_sampling(graph.ref, ptr(i), E, N, int(seed) & (2**64 - 1),
+                                                        int(max_tries), ptr(k), ptr(failed), stream_of(dev)),
+                  "dl_structured_negative_sampling")
+            if int(failed.item()):
+                raise RuntimeError(f"{int(failed.item())} edges start at a node adjacent to every node: no negative exists")
+    return i, j, k
+
+
+def roc_auc_stats(score, labels):
+    """-> float64 tensor [5] on the device: (auc, n_pos, n_neg, n_nan, 2U) -- see dl_roc_auc.  No host sync."""
+    dev = score.device
+    require_cuda(score, "score")
+    if score.dtype != torch.float32:
+        raise TypeError("score must be float32")
+    P = int(score.numel())
+    score = score.contiguous()
+    labels = labels.to(torch.float32).contiguous()
+    L = lib()
+    with torch.cuda.device(dev):
+        out = torch.empty(5, dtype=torch.float64, device=dev)
+        ws_bytes = int(L.dl_roc_auc_workspace_bytes(P))
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        check(L.dl_roc_auc(ptr(score), ptr(labels), P, ptr(out), ptr(ws), ws_bytes, stream_of(dev)), "dl_roc_auc")
+    return out
+
+
+def roc_auc(score, labels) -> float:
+    """sklearn.metrics.roc_auc_score(labels, score) for binary labels, computed on the device
+    (main_disentangled.py:204,219).  Raises ValueError where sklearn does (one class only, NaN)."""
+    auc, n_pos, n_neg, n_nan, _ = roc_auc_stats(score, labels).tolist()
+    if n_nan:
+        raise ValueError("Input contains NaN.")
+    if n_pos == 0 or n_neg == 0:
+        raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
+    return auc
+
+
 class _LinkBCELoss(torch.autograd.Function):
     """Whole hot path as one differentiable op with explicit buffer reuse (4 [N,K,d] buffers live):
     attention -> aggregation -> pair scores -> weighted BCE -> decoder backward -> factor backward.

@@ -215,6 +215,27 @@ int64_t dl_link_bce_workspace_bytes(void);
 int dl_link_bce(const float* prob, const float* labels, const float* weights, int64_t P, float* dS,
                 float* loss, void* ws, int64_t ws_bytes, dl_stream_t stream);
 
+/* ---- ROC-AUC of a score list ----------------------------------------------------------------
+ * [ref: main_disentangled.py:202-204,217-219 -- sklearn.metrics.roc_auc_score(y, a_pred[mask == 1])]
+ * labels: 0 / non-zero floats.  out: 5 doubles on the device = { auc, n_pos, n_neg, n_nan, 2U } where
+ * 2U = sum over positives of 2 * #(negatives below) + #(negatives tied) (an exact integer) and
+ * auc = 2U / (2 n_pos n_neg); auc is NaN when a class is empty or a score is NaN (sklearn raises).
+ * P < 2^31.  ws: >= dl_roc_auc_workspace_bytes(P) bytes of device scratch. */
+int64_t dl_roc_auc_workspace_bytes(int64_t P);
+int dl_roc_auc(const float* score, const float* labels, int64_t P, double* out, void* ws, int64_t ws_bytes,
+               dl_stream_t stream);
+
+/* ---- structured negative sampling ---------------------------------------------------------
+ * [ref: main_disentangled.py:160 -- torch_geometric.utils.structured_negative_sampling(edge_index)]
+ * For every edge e with source src[e]: k_out[e] ~ U[0, num_nodes) redrawn while (src[e], k) is an
+ * entry of g (the CSR of the DIRECTED edge columns, dl_csr_build_rect with symmetrize = 0).  Draw t of
+ * edge e is Philox4x32-10(key = seed, counter = (e, t)) -> r = (c1 << 32 | c0), k = (r * num_nodes) >> 64.
+ * After max_tries rejected draws the first non-neighbour of the row is used; a row adjacent to every
+ * node yields -1 and is counted in n_failed[0] (device int). */
+int dl_structured_negative_sampling(const dl_graph* g_host, const int64_t* src, int64_t E, int64_t num_nodes,
+                                    uint64_t seed, int max_tries, int64_t* k_out, int* n_failed,
+                                    dl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,3 +158,99 @@ def test_link_bce_kernel_vs_oracle_and_torch(P):
         # bitwise run-to-run determinism of the reduction
         l2, _ = ops.link_bce(prob.detach(), yt, wt)
         assert l2.item() == loss.item()
+
+
+@pytest.mark.parametrize("case,P", [("distinct", 1000), ("ties", 100000), ("saturated", 1 << 20),
+                                    ("signed_zero", 5000), ("one_tie_group", 70000), ("distinct", 1 << 22)])
+def test_roc_auc_kernel_vs_oracle_and_sklearn(case, P):
+    """dl_roc_auc: the integer 2U is bit-exact against the oracle, the AUC matches sklearn's
+    roc_auc_score to 1e-12 (the script's metric, main_disentangled.py:204,219)."""
+    from disenlink_b200 import ops
+    from oracle import oracle
+    from sklearn.metrics import roc_auc_score
+    rng = np.random.default_rng(P)
+    y = (rng.random(P) < 0.17).astype(np.float32)
+    if case == "distinct":
+        sc = rng.standard_normal(P).astype(np.float32)
+    elif case == "ties":
+        sc = (rng.integers(0, 211, P) / 211.0).astype(np.float32)
+    elif case == "saturated":
+        sc = (1.0 / (1.0 + np.exp(-(rng.standard_normal(P) * 30)))).astype(np.float32)
+    elif case == "signed_zero":
+        sc = np.where(rng.random(P) < 0.5, np.float32(0.0), np.float32(-0.0)).astype(np.float32)
+        sc[:100] = rng.standard_normal(100).astype(np.float32)
+    else:
+        sc = np.full(P, 0.25, np.float32)
+        sc[:7] = [0.1, 0.9, 0.25, 0.3, 0.2, 0.25, 1.0]
+    out = ops.roc_auc_stats(torch.from_numpy(sc).to(DEV), torch.from_numpy(y).to(DEV)).cpu().numpy()
+    auc, two_u, n_pos, n_neg = oracle.roc_auc(sc, y)
+    assert (int(out[1]), int(out[2]), int(out[3])) == (n_pos, n_neg, 0)
+    assert int(out[4]) == two_u
+    assert out[0] == auc
+    assert abs(out[0] - roc_auc_score(y, sc)) < 1e-12
+    assert ops.roc_auc(torch.from_numpy(sc).to(DEV), torch.from_numpy(y).to(DEV)) == auc
+
+
+def test_roc_auc_error_cases():
+    from disenlink_b200 import ops
+    sc = torch.rand(100, device=DEV)
+    with pytest.raises(ValueError):
+        ops.roc_auc(sc, torch.ones(100, device=DEV))
+    with pytest.raises(ValueError):
+        ops.roc_auc(sc, torch.zeros(100, device=DEV))
+    bad = sc.clone()
+    bad[3] = float("nan")
+    lab = (torch.rand(100, device=DEV) < 0.5).float()
+    lab[0], lab[1] = 1.0, 0.0
+    with pytest.raises(ValueError):
+        ops.roc_auc(bad, lab)
+    with pytest.raises(ValueError):
+        ops.roc_auc(torch.empty(0, device=DEV), torch.empty(0, device=DEV))
+
+
+@pytest.mark.parametrize("n,e,seed", [(50, 400, 0), (300, 6000, 7), (20000, 200000, 123456789012345)])
+def test_structured_negative_sampling_vs_oracle(n, e, seed):
+    """dl_structured_negative_sampling == the numpy oracle bit for bit; PyG's contract holds."""
+    from disenlink_b200 import ops
+    from oracle import oracle
+    rng = np.random.default_rng(n)
+    src, dst = rng.integers(0, n, e), rng.integers(0, n, e)
+    ei = torch.from_numpy(np.stack([src, dst])).to(DEV)
+    i, j, k = ops.structured_negative_sampling(ei, n, seed=seed)
+    assert np.array_equal(i.cpu().numpy(), src) and np.array_equal(j.cpu().numpy(), dst)
+    assert np.array_equal(k.cpu().numpy(), oracle.structured_negative_sampling(src, dst, n, seed=seed))
+    keys = set((src * n + dst).tolist())
+    assert all((int(a) * n + int(b)) not in keys for a, b in zip(src, k.cpu().numpy()))
+
+
+def test_structured_negative_sampling_dense_rows():
+    """A node adjacent to all but one node always gets that node (fallback after rejected draws);
+    a node adjacent to every node has no negative: error, like an endless loop in PyG."""
+    from disenlink_b200 import ops
+    from oracle import oracle
+    n = 40
+    src = np.concatenate([np.zeros(n - 1, np.int64), np.array([1, 2], np.int64)])
+    dst = np.concatenate([np.delete(np.arange(n), 17), np.array([5, 9], np.int64)])
+    ei = torch.from_numpy(np.stack([src, dst])).to(DEV)
+    i, j, k = ops.structured_negative_sampling(ei, n, seed=3, max_tries=4)
+    k = k.cpu().numpy()
+    assert (k[:n - 1] == 17).all()
+    assert np.array_equal(k, oracle.structured_negative_sampling(src, dst, n, seed=3, max_tries=4))
+    full = torch.from_numpy(np.stack([np.zeros(n, np.int64), np.arange(n)])).to(DEV)
+    with pytest.raises(RuntimeError):
+        ops.structured_negative_sampling(full, n, seed=0, max_tries=2)
+
+
+def test_structured_negative_sampling_large_properties():
+    """2e7 edges: no sampled (i, k) is an edge (checked through the CSR on the device)."""
+    from disenlink_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(5)
+    n, e = 2_000_000, 20_000_000
+    ei = torch.randint(0, n, (2, e), device=DEV, generator=g)
+    i, j, k = ops.structured_negative_sampling(ei, n, seed=11)
+    assert int(k.min()) >= 0 and int(k.max()) < n
+    edge_keys = torch.unique(ei[0] * n + ei[1])
+    pos = torch.searchsorted(edge_keys, i * n + k).clamp_(max=edge_keys.numel() - 1)
+    assert not bool((edge_keys[pos] == i * n + k).any())
+    cnt = torch.bincount(k, minlength=n).float()
+    assert float(((cnt - e / n) ** 2 / (e / n)).sum()) < 1.2 * n

@@ -170,3 +170,55 @@ def test_bce_weighted_matches_torch(oracle):
     loss, dS = oracle.bce_weighted(p.detach().numpy(), y, w)
     assert abs(loss - ref.item()) <= 2e-6 * abs(ref.item())
     assert np.abs(dS - S.grad.numpy()).max() <= 1e-6 * float(S.grad.abs().max())
+
+
+@pytest.mark.parametrize("case", ["distinct", "ties", "saturated", "signed_zero"])
+def test_roc_auc_oracle_matches_sklearn(oracle, case):
+    """oracle.roc_auc against sklearn.metrics.roc_auc_score (the function the script calls,
+    main_disentangled.py:204,219)."""
+    from sklearn.metrics import roc_auc_score
+    rng = np.random.default_rng(11)
+    n = 5000
+    y = (rng.random(n) < 0.2).astype(np.float32)
+    if case == "distinct":
+        sc = rng.random(n).astype(np.float32)
+    elif case == "ties":
+        sc = (rng.integers(0, 37, n) / 37.0).astype(np.float32)
+    elif case == "saturated":
+        sc = 1.0 / (1.0 + np.exp(-(rng.standard_normal(n) * 30))).astype(np.float32)     # many exact 0 / 1
+        sc = sc.astype(np.float32)
+    else:
+        sc = np.where(rng.random(n) < 0.5, np.float32(0.0), np.float32(-0.0)).astype(np.float32)
+        sc[:100] = rng.standard_normal(100).astype(np.float32)
+    auc, two_u, n_pos, n_neg = oracle.roc_auc(sc, y)
+    assert n_pos == int(y.sum()) and n_neg == n - n_pos
+    assert abs(auc - roc_auc_score(y, sc)) < 1e-12
+
+
+def test_philox_known_answers(oracle):
+    """Random123's published known-answer vectors for Philox4x32-10 pin the draw stream of the
+    negative sampler."""
+    z = oracle.philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(x[0]) for x in z] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xFFFFFFFF
+    o = oracle.philox4x32_10([f], [f], [f], [f], f, f)
+    assert [int(x[0]) for x in o] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    p = oracle.philox4x32_10([0x243f6a88], [0x85a308d3], [0x13198a2e], [0x03707344], 0xa4093822, 0x299f31d0)
+    assert [int(x[0]) for x in p] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_structured_negative_sampling_oracle_properties(oracle):
+    """PyG semantics (main_disentangled.py:160): (i, k) is never an edge column, k is uniform over
+    the non-neighbours, the stream depends on the seed only."""
+    rng = np.random.default_rng(2)
+    n, e = 300, 6000
+    src, dst = rng.integers(0, n, e), rng.integers(0, n, e)
+    k = oracle.structured_negative_sampling(src, dst, n, seed=7)
+    keys = set((src * n + dst).tolist())
+    assert all((int(i) * n + int(kk)) not in keys for i, kk in zip(src, k))
+    assert k.min() >= 0 and k.max() < n
+    assert np.array_equal(k, oracle.structured_negative_sampling(src, dst, n, seed=7))
+    assert not np.array_equal(k, oracle.structured_negative_sampling(src, dst, n, seed=8))
+    # roughly uniform: chi-square over nodes, 6000 draws into 300 bins (mean 20)
+    cnt = np.bincount(k, minlength=n)
+    assert ((cnt - e / n) ** 2 / (e / n)).sum() < 2.0 * n
