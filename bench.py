@@ -395,12 +395,15 @@ def run_native(args):
         prob_host = torch.empty(P, dtype=torch.float32).pin_memory()
         Zd = torch.empty(N, K, d, dtype=torch.float32, device=dev)
 
+        last = {}
+
         def e2e_step():
             Zd.copy_(Z_host, non_blocking=True)
             Zg = Zd.requires_grad_(True)
             loss, prob, _ = ops.link_bce_loss(Zg, g_full, batch, lab, wts, beta, T)
             loss.backward()
             prob_host.copy_(prob, non_blocking=True)
+            last["prob"] = prob
             val = loss.item()
             Zg.grad = None
             Zd.requires_grad_(False)
@@ -418,6 +421,32 @@ def run_native(args):
                "h2d_bytes_per_step": int(N * D * 4), "d2h_bytes_per_step": int(P * 4 + 4),
                "api": "ops.link_bce_loss(Z, graph, pairs, labels, weights).backward(); Z from pinned host "
                       "memory, loss + P scores read back", "loss": e2e_loss}
+
+    # ---- the evaluation-side kernels of SURVEY 8(f) on the same data: AUC of the P scores, one
+    # round of structured negative sampling against the resident CSR (device-timed, outside the step) ----
+    extras = None
+    if e2e is not None:
+        def timed(fn, reps=2):
+            fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            a.record()
+            for _ in range(reps):
+                out = fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / reps, out
+        prob_d = last["prob"]
+        auc_ms, auc_out = timed(lambda: ops.roc_auc_stats(prob_d, lab))
+        n_src = min(g_full.nnz, 100_000_000)
+        src64 = g_full.erow[:n_src].to(torch.int64)
+        ei = torch.stack([src64, g_full.col[:n_src].to(torch.int64)])
+        ns_ms, ns_out = timed(lambda: ops.structured_negative_sampling(ei, N, seed=1, graph=g_full))
+        extras = {"roc_auc": {"pairs": P, "ms": round(auc_ms, 3), "pairs_per_s": P / (auc_ms * 1e-3),
+                              "auc": float(auc_out[0].item())},
+                  "structured_negative_sampling": {"edges": n_src, "ms": round(ns_ms, 3),
+                                                   "edges_per_s": n_src / (ns_ms * 1e-3)}}
+        del ei, src64, ns_out
 
     if rank != 0:
         if world > 1:
@@ -443,6 +472,8 @@ def run_native(args):
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if extras is not None:
+        line["next_rows"] = extras
     if cb is not None:
         line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
