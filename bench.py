@@ -352,11 +352,11 @@ def run_native(args):
     # node-major decoder backward: per incidence the other endpoint's Z and H rows + 3 ids/floats,
     # per node 2 rows in and 2 rows out (less than SURVEY's scatter-form P*(32D+16): see DESIGN.md)
     ab["pair_bwd"] = int(step.inc.nnz) * (8 * D + 12) + part.n_local * 16 * D
-    # kernels of libdisenlink_b200.so per step (streaming path): attention = routing + row sums +
-    # chain + empty rows (4); aggregation = gather + chain + empty rows (3); pair scoring fwd (1);
+    # kernels of libdisenlink_b200.so per step (streaming path): attention = routing with fused row sums +
+    # chain + empty rows (3); aggregation = gather + chain + empty rows (3); pair scoring fwd (1);
     # decoder backward = stream + chain + empty nodes (3); backward pass 1 (3); backward pass 2 =
     # stream + chain (2); weighted BCE forward+backward (2)
-    launches_per_step = 18
+    launches_per_step = 17
     kernels = {}
     for kname in KERNEL_PHASES:
         ms = phase_ms[kname]

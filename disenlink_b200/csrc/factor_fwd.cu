@@ -333,6 +333,12 @@ int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
   bool stream_tried = false;
+  // factor-per-lane kernel (attn_fl.cu): routing and row sums in one launch; DL_NO_FL=1 disables it
+  if (g.erow && g.nnz > 0 && !getenv("DL_NO_STREAM") && !getenv("DL_NO_FL") && !getenv("DL_NO_FL_ATTN")) {
+    rc = dl_launch_attn_fl(g, Z, K, d, T, kstar, w, s, hub_ws, st);
+    if (rc == DL_OK) return DL_OK;
+    if (rc != -1000) return rc;
+  }
   if (g.erow && g.nnz > 0 && !getenv("DL_NO_STREAM")) {
     rc = dl_launch_attn_stream(g, g.erow, Z, K, d, T, kstar, w, s, hub_ws, st);
     stream_tried = (rc != -1000);

@@ -461,3 +461,16 @@ int dl_gather_chain_pair(const DlGraphDev& g, int K, int d, float* scratch, floa
   DL_LAUNCH_CHECK();
   return DL_OK;
 }
+
+// chain fix-up + empty rows for row sums produced by attn_fl.cu (mode 2: W = K, 0 -> 1)
+int dl_gather_chain_rowsum(const DlGraphDev& g, int K, float* scratch, float* s_out, cudaStream_t st) {
+  const long long RE = (long long)DL_CH * DL_RANGE;
+  const long long n_ranges = (g.nnz + RE - 1) / RE;
+  k_gather_chain<<<small_grid(n_ranges), DL_CTA, 0, st>>>(g, 2, K, 1, scratch, nullptr, nullptr, nullptr, 0.0f,
+                                                          0.0f, s_out, nullptr, scratch + (size_t)n_ranges * 2 * K);
+  DL_LAUNCH_CHECK();
+  k_gather_empty_rows<<<small_grid((g.N + 31) / 32), DL_CTA, 0, st>>>(g, 2, K, 1, nullptr, nullptr, nullptr,
+                                                                     0.0f, 0.0f, s_out, nullptr);
+  DL_LAUNCH_CHECK();
+  return DL_OK;
+}
