@@ -393,34 +393,79 @@ def run_native(args):
         del Z
         torch.cuda.empty_cache()
         prob_host = torch.empty(P, dtype=torch.float32).pin_memory()
-        Zd = torch.empty(N, K, d, dtype=torch.float32, device=dev)
-
+        # Input staging: Z comes from pinned host memory every step.  Two device buffers and a copy
+        # stream let the upload of step t+1 overlap the kernels of step t (every timed step still
+        # issues, and the timed region completes, one 4*N*D-byte upload and one P-float read-back);
+        # with a single buffer (not enough memory for two) the upload is serial with the kernels.
+        Zbufs = [torch.empty(N, K, d, dtype=torch.float32, device=dev)]
+        try:
+            Zbufs.append(torch.empty(N, K, d, dtype=torch.float32, device=dev))
+        except torch.cuda.OutOfMemoryError:
+            pass
+        nb = len(Zbufs)
+        copy_stream = torch.cuda.Stream(dev)
+        ready = [torch.cuda.Event() for _ in range(nb)]
+        free = [torch.cuda.Event() for _ in range(nb)]
+        for ev in free:
+            ev.record(torch.cuda.current_stream(dev))
         last = {}
 
-        def e2e_step():
-            Zd.copy_(Z_host, non_blocking=True)
-            Zg = Zd.requires_grad_(True)
+        def upload(slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[slot])          # the kernels that read this buffer are done
+                Zbufs[slot].copy_(Z_host, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def e2e_step(i):
+            cur = torch.cuda.current_stream(dev)
+            slot = i % nb
+            if nb == 1:
+                upload(0)
+            else:
+                upload((i + 1) % nb)                        # next step's input
+            cur.wait_event(ready[slot])
+            Zg = Zbufs[slot].requires_grad_(True)
             loss, prob, _ = ops.link_bce_loss(Zg, g_full, batch, lab, wts, beta, T)
             loss.backward()
+            free[slot].record(cur)
             prob_host.copy_(prob, non_blocking=True)
             last["prob"] = prob
             val = loss.item()
             Zg.grad = None
-            Zd.requires_grad_(False)
+            Zbufs[slot].requires_grad_(False)
             return val
 
-        for _ in range(max(args.warmup, 1)):
-            e2e_step()
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_loss = e2e_step()
-        torch.cuda.synchronize(dev)
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        def e2e_run(n_steps, i0):
+            for i in range(i0, i0 + n_steps):
+                val = e2e_step(i)
+            torch.cuda.synchronize(dev)                     # all streams: the last upload included
+            return val
+
+        try:
+            if nb > 1:
+                upload(0)
+            n_warm = max(args.warmup, 1)
+            e2e_run(n_warm, 0)
+            t0 = time.perf_counter()
+            e2e_loss = e2e_run(args.steps, n_warm)
+            e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        except torch.cuda.OutOfMemoryError:
+            # the second input buffer did not leave room for the step's own buffers: serial staging
+            del Zbufs[1:]
+            nb = 1
+            last.clear()
+            torch.cuda.empty_cache()
+            e2e_run(max(args.warmup, 1), 0)
+            t0 = time.perf_counter()
+            e2e_loss = e2e_run(args.steps, 0)
+            e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         e2e = {"value": g_full.nnz / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": round(e2e_ms, 3),
                "h2d_bytes_per_step": int(N * D * 4), "d2h_bytes_per_step": int(P * 4 + 4),
                "api": "ops.link_bce_loss(Z, graph, pairs, labels, weights).backward(); Z from pinned host "
-                      "memory, loss + P scores read back", "loss": e2e_loss}
+                      "memory, loss + P scores read back",
+               "input_staging": ("double-buffered on a copy stream: the upload of step t+1 overlaps the kernels "
+                                 "of step t" if nb > 1 else "single buffer: upload serial with the kernels"),
+               "loss": e2e_loss}
 
     # ---- the evaluation-side kernels of SURVEY 8(f) on the same data: AUC of the P scores, one
     # round of structured negative sampling against the resident CSR (device-timed, outside the step) ----
