@@ -242,9 +242,29 @@ class Disentangle(nn.Module):
         self.dense_limit = dense_limit
 
     def project(self, x: torch.Tensor) -> torch.Tensor:
-        """Z [N,K,d] = the K factor MLPs of model.py:106 (library GEMMs, fp32 -- TF32 would break
-        the 1e-5 parity target)."""
-        return torch.stack([f(x) for f in self.factors], dim=1)
+        """Z [N,K,d] = the K factor MLPs of model.py:106, batched: one [N,F] x [F,K*nhid] GEMM for the
+        K first layers (a sparse-dense product when x is a sparse tensor: bag-of-words features are
+        ~1 % dense) and one batched [K] x ([N,nhid] x [nhid,d]) product for the second layers, written
+        straight into the [N,K,d] layout.  The parameters stay the per-factor nn.Linear modules of
+        the reference (same state_dict); the stacked weights are views rebuilt per call, so autograd
+        routes the gradients back to them.  Library GEMMs, fp32 -- TF32 would break the 1e-5 parity
+        target."""
+        K = len(self.factors)
+        first = [f.mlp if isinstance(f, Factor) else f.mlp1 for f in self.factors]
+        W1 = torch.cat([m.weight for m in first], dim=0)              # [K*nhid, F]
+        b1 = torch.cat([m.bias for m in first], dim=0)
+        if x.is_sparse or x.layout == torch.sparse_csr:
+            hid = torch.sparse.mm(x, W1.t()) + b1
+        else:
+            hid = torch.addmm(b1, x, W1.t())                          # [N, K*nhid]
+        N = hid.shape[0]
+        if isinstance(self.factors[0], Factor):
+            return hid.view(N, K, -1)
+        hid = F.relu(hid).view(N, K, -1).transpose(0, 1)              # [K, N, nhid]
+        W2 = torch.stack([f.mlp2.weight for f in self.factors], dim=0)  # [K, d, nhid]
+        b2 = torch.stack([f.mlp2.bias for f in self.factors], dim=0)    # [K, d]
+        Z = torch.baddbmm(b2.unsqueeze(1), hid, W2.transpose(1, 2))   # [K, N, d]
+        return Z.transpose(0, 1).contiguous()
 
     def embed(self, x: torch.Tensor, adj: AdjLike):
         """-> (Z [N,K,d], H [N,K,d], graph)"""
