@@ -88,8 +88,8 @@ template <int K_, int d_>
 __global__ void __launch_bounds__(FlCfg<K_, d_>::THREADS, 1)
 k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restrict__ G,
                const unsigned char* __restrict__ kstar, const float* __restrict__ s,
-               const float* __restrict__ r, float omb, float T, float* __restrict__ dZ,
-               float* __restrict__ carry) {
+               const float* __restrict__ r, const float* __restrict__ sj, float omb, float T,
+               float* __restrict__ dZ, float* __restrict__ carry) {
   using C = FlCfg<K_, d_>;
   constexpr int K = C::K, d = C::d, D = C::D, LPE = C::LPE, EPS = C::EPS, QPC = C::QPC, C4 = C::C4;
   constexpr int ROWS = C::ROWS, STAGE_B = C::STAGE_B, OWN_B = C::OWN_B;
@@ -117,7 +117,10 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
     m.row = -1; m.col = 0; m.info = 0; m.sj = 1.0f; m.rj = 0.0f;
     if (cc >= 0) {
       const long long e = cc * DL_CH + lane;
-      if (e < g.nnz) { m.row = __ldg(g.erow + e); m.col = __ldg(g.col + e); m.info = __ldg(kstar + e); }
+      if (e < g.nnz) {
+        m.row = __ldg(g.erow + e); m.col = __ldg(g.col + e); m.info = __ldg(kstar + e);
+        if (sj) m.sj = __ldg(sj + e);        // s[col, kstar] as the forward saw it: no gather needed
+      }
     }
   };
   // second half of a chunk's metadata, once row / col / kstar have arrived: the s[j,k], r[j,k]
@@ -126,7 +129,7 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
     const int ks = m.info;
 #ifndef FL_EXP_NOSR
     if (m.row >= 0) {
-      m.sj = __ldg(s + (long long)m.col * K + ks);
+      if (!sj) m.sj = __ldg(s + (long long)m.col * K + ks);
       m.rj = __ldg(r + (long long)m.col * K + ks);
     }
 #endif
@@ -369,7 +372,8 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
 template <int K_, int d_>
 struct FlLaunch {
   static int run(const DlGraphDev& g, const float* Z, const float* G, const unsigned char* kstar,
-                 const float* s, const float* r, float omb, float T, float* dZ, float* carry, cudaStream_t st) {
+                 const float* s, const float* r, const float* sj, float omb, float T, float* dZ, float* carry,
+                 cudaStream_t st) {
     using C = FlCfg<K_, d_>;
     int dev = 0, sms = 0;
     DL_CUDA_TRY(cudaGetDevice(&dev));
@@ -381,7 +385,7 @@ struct FlLaunch {
     long long grid = (n_ranges + C::NW - 1) / C::NW;
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
-    k_bwd_edges_fl<K_, d_><<<(int)grid, C::THREADS, C::SMEM, st>>>(g, Z, G, kstar, s, r, omb, T, dZ, carry);
+    k_bwd_edges_fl<K_, d_><<<(int)grid, C::THREADS, C::SMEM, st>>>(g, Z, G, kstar, s, r, sj, omb, T, dZ, carry);
     DL_LAUNCH_CHECK();
     return DL_OK;
   }
@@ -391,13 +395,13 @@ struct FlLaunch {
 
 // returns -1000 when (K, d) has no factor-per-lane instantiation; scratch as for bwd_stream.cu
 int dl_launch_bwd_edges_fl(const DlGraphDev& g, const float* Z, const float* G, const unsigned char* kstar,
-                           const float* s, const float* r, int K, int d, float omb, float T, float* dZ,
-                           float* scratch, cudaStream_t st) {
+                           const float* s, const float* r, const float* sj, int K, int d, float omb, float T,
+                           float* dZ, float* scratch, cudaStream_t st) {
   if (!g.erow || g.nnz == 0 || !scratch) return -1000;
   int rc = -1000;
-  if (K == 8 && d == 16) rc = FlLaunch<8, 16>::run(g, Z, G, kstar, s, r, omb, T, dZ, scratch, st);
-  else if (K == 8 && d == 8) rc = FlLaunch<8, 8>::run(g, Z, G, kstar, s, r, omb, T, dZ, scratch, st);
-  else if (K == 5 && d == 16) rc = FlLaunch<5, 16>::run(g, Z, G, kstar, s, r, omb, T, dZ, scratch, st);
+  if (K == 8 && d == 16) rc = FlLaunch<8, 16>::run(g, Z, G, kstar, s, r, sj, omb, T, dZ, scratch, st);
+  else if (K == 8 && d == 8) rc = FlLaunch<8, 8>::run(g, Z, G, kstar, s, r, sj, omb, T, dZ, scratch, st);
+  else if (K == 5 && d == 16) rc = FlLaunch<5, 16>::run(g, Z, G, kstar, s, r, sj, omb, T, dZ, scratch, st);
   if (rc != DL_OK) return rc;
   return dl_gather_chain_add(g, K, d, scratch, dZ, st);
 }

@@ -308,6 +308,14 @@ inline int fixup_blocks(long long n) {
 
 }  // namespace
 
+// per-entry copy of s[col, kstar] (sj_out) for the paths that do not write it on the way
+static __global__ void k_entry_sj(DlGraphDev g, const unsigned char* __restrict__ kstar, const float* __restrict__ s,
+                           int K, float* __restrict__ sj) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < g.nnz; e += stride)
+    sj[e] = __ldg(s + (long long)__ldg(g.col + e) * K + __ldg(kstar + e));
+}
+
 extern "C" {
 
 size_t dl_hub_scratch_floats(const dl_graph* g_host, int64_t width) {
@@ -369,7 +377,7 @@ int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float
 
 int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
                        const float* w, const float* s, int K, int d, float beta,
-                       float one_minus_beta, float* H, float* hub_ws, dl_stream_t stream) {
+                       float one_minus_beta, float* H, float* sj_out, float* hub_ws, dl_stream_t stream) {
   if (!dl_graph_ok(g_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
   if (g_host->N == 0) return DL_OK;
   if (!Z || !s || !H || (g_host->nnz > 0 && (!kstar || !w))) return DL_EINVAL;
@@ -379,9 +387,13 @@ int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* ks
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
   if (!getenv("DL_NO_STREAM"))
-    rc = dl_launch_gather_stream(0, g, Z, Z, kstar, w, s, K, d, beta, one_minus_beta, H, nullptr, hub_ws, st);
+    rc = dl_launch_gather_stream(0, g, Z, Z, kstar, w, s, K, d, beta, one_minus_beta, H, sj_out, hub_ws, st);
   if (rc == DL_OK) return DL_OK;             // carries, chained rows and empty rows all handled
   if (rc != -1000) return rc;
+  if (sj_out && g.nnz > 0) {                 // the other paths do not produce sj on the way
+    k_entry_sj<<<fixup_blocks(g.nnz), 256, 0, st>>>(g, kstar, s, K, sj_out);
+    DL_LAUNCH_CHECK();
+  }
   rc = dl_launch_slice_gather(0, g, n_items, Z, Z, kstar, w, s, K, d, beta, one_minus_beta, H, nullptr,
                               hub_ws, st);
   if (rc == -1000) {

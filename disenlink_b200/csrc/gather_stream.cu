@@ -316,6 +316,9 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
       tail_open = R1 < g.nnz && __ldg(g.erow + R1) == __ldg(g.erow + R1 - 1);
     }
 
+    // MODE 0 has no r output: the pointer carries the optional per-entry copy of s[col, kstar]
+    // (sj_out of dl_factor_spmm_fwd) that lets backward pass 2 skip this gather
+    if (MODE == 0 && r != nullptr && mA.row >= 0) r[c * DL_CH + lane] = sjA;
     const float coefA = (MODE == 0) ? __fdiv_rn(mA.wv, sjA) : mA.wv;
     const unsigned vmask = __ballot_sync(DL_FULL, mA.row >= 0);
     const int cnt = __popc(vmask);
@@ -427,11 +430,12 @@ int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const
   DL_DISPATCH_SHAPES()
 #undef BODY_MACRO
   if (rc != DL_OK) return rc;
-  k_gather_chain<<<small_grid(n_ranges), DL_CTA, 0, st>>>(g, mode, K, d, carry, Z, SRC, s, beta, omb, OUT, r,
-                                                          chain);
+  float* r_node = (mode == 0) ? nullptr : r;       // in mode 0 `r` is the per-entry sj output
+  k_gather_chain<<<small_grid(n_ranges), DL_CTA, 0, st>>>(g, mode, K, d, carry, Z, SRC, s, beta, omb, OUT,
+                                                          r_node, chain);
   DL_LAUNCH_CHECK();
   k_gather_empty_rows<<<small_grid((g.N + 31) / 32), DL_CTA, 0, st>>>(g, mode, K, d, Z, SRC, s, beta, omb,
-                                                                     OUT, r);
+                                                                     OUT, r_node);
   DL_LAUNCH_CHECK();
   return DL_OK;
 }

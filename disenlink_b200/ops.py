@@ -56,15 +56,20 @@ def edge_attn_fwd(graph: Graph, Z: torch.Tensor, T: float = 1.0, out=None):
     return kstar[:graph.nnz], w[:graph.nnz], s
 
 
-def factor_spmm_fwd(graph: Graph, Z, kstar, w, s, beta: float, out=None):
-    """-> H [N,K,d].  [ref: model.py:75]"""
+def _optr(t):
+    return ptr(t) if t is not None else None
+
+
+def factor_spmm_fwd(graph: Graph, Z, kstar, w, s, beta: float, out=None, sj=None):
+    """-> H [N,K,d].  [ref: model.py:75]  `sj` = optional f32 [nnz] buffer that receives s[col, kstar]
+    per entry (pass it on to factor_bwd / factor_bwd_edges)."""
     K, d = _check_Z(Z, graph.n_global)
     Z = Z.contiguous()
     dev = Z.device
     with torch.cuda.device(dev):
         H = torch.empty_like(Z) if out is None else out
         check(lib().dl_factor_spmm_fwd(graph.ref, ptr(Z), ptr(kstar), ptr(w), ptr(s), K, d,
-                                       float(beta), one_minus(beta), ptr(H),
+                                       float(beta), one_minus(beta), ptr(H), _optr(sj),
                                        ptr(graph.hub_scratch(K * d)), stream_of(dev)),
               "dl_factor_spmm_fwd")
     return H
@@ -81,18 +86,18 @@ def factor_bwd_gather(graph: Graph, Z, G, kstar, w, s, beta: float, dZ, r):
               "dl_factor_bwd_gather")
 
 
-def factor_bwd_edges(graph: Graph, Z, G, kstar, w, s, r, beta: float, T: float, dZ):
+def factor_bwd_edges(graph: Graph, Z, G, kstar, w, s, r, beta: float, T: float, dZ, sj=None):
     """Pass 2 of the backward: dZ += attention-weight terms (needs r of every neighbour)."""
     K, d = _check_Z(Z, graph.n_global)
     dev = Z.device
     with torch.cuda.device(dev):
-        check(lib().dl_factor_bwd_edges(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), ptr(r), K, d,
+        check(lib().dl_factor_bwd_edges(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), ptr(r), _optr(sj), K, d,
                                         one_minus(beta), float(T), ptr(dZ),
                                         ptr(graph.hub_scratch(K * d)), stream_of(dev)),
               "dl_factor_bwd_edges")
 
 
-def factor_bwd(graph: Graph, Z, G, kstar, w, s, beta: float, T: float = 1.0, dZ=None, r=None):
+def factor_bwd(graph: Graph, Z, G, kstar, w, s, beta: float, T: float = 1.0, dZ=None, r=None, sj=None):
     """dL/dZ through attention + aggregation given G = dL/dH; accumulated into dZ if given.
     -> (dZ, r).  [ref: autograd of model.py:56-75]"""
     K, d = _check_Z(Z, graph.n_global)
@@ -104,7 +109,7 @@ def factor_bwd(graph: Graph, Z, G, kstar, w, s, beta: float, T: float = 1.0, dZ=
             dZ = torch.zeros_like(Z)
         if r is None:
             r = torch.empty(graph.n_global, K, dtype=torch.float32, device=dev)
-        check(lib().dl_factor_bwd(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d,
+        check(lib().dl_factor_bwd(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), _optr(sj), K, d,
                                   float(beta), one_minus(beta), float(T), ptr(dZ), ptr(r),
                                   ptr(graph.hub_scratch(K * d)), stream_of(dev)), "dl_factor_bwd")
     return dZ, r
@@ -199,8 +204,9 @@ class _FactorAggregate(torch.autograd.Function):
     def forward(ctx, Z, graph, beta, T):
         Zc = Z.contiguous()
         kstar, w, s = edge_attn_fwd(graph, Zc, T)
-        H = factor_spmm_fwd(graph, Zc, kstar, w, s, beta)
-        ctx.graph, ctx.beta, ctx.T = graph, float(beta), float(T)
+        sj = torch.empty(max(graph.nnz, 1), dtype=torch.float32, device=Zc.device) if Z.requires_grad else None
+        H = factor_spmm_fwd(graph, Zc, kstar, w, s, beta, sj=sj)
+        ctx.graph, ctx.beta, ctx.T, ctx.sj = graph, float(beta), float(T), sj
         ctx.save_for_backward(Zc, kstar, w, s)
         ctx.mark_non_differentiable(kstar, w, s)
         return H, kstar, w, s
@@ -208,7 +214,7 @@ class _FactorAggregate(torch.autograd.Function):
     @staticmethod
     def backward(ctx, G, _gk, _gw, _gs):
         Z, kstar, w, s = ctx.saved_tensors
-        dZ, _ = factor_bwd(ctx.graph, Z, G.contiguous(), kstar, w, s, ctx.beta, ctx.T)
+        dZ, _ = factor_bwd(ctx.graph, Z, G.contiguous(), kstar, w, s, ctx.beta, ctx.T, sj=ctx.sj)
         return dZ, None, None, None
 
 
@@ -335,16 +341,17 @@ class _LinkBCELoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Z, graph, batch, labels, weights, beta, T):
         Zc = Z.detach().contiguous()
-        kstar, w, s = edge_attn_fwd(graph, Zc, T)
-        H = factor_spmm_fwd(graph, Zc, kstar, w, s, beta)
-        _, prob = pair_score_fwd(Zc, H, batch, T, want_logit=False)
         need_grad = ctx.needs_input_grad[0]
+        kstar, w, s = edge_attn_fwd(graph, Zc, T)
+        sj = torch.empty(max(graph.nnz, 1), dtype=torch.float32, device=Zc.device) if need_grad else None
+        H = factor_spmm_fwd(graph, Zc, kstar, w, s, beta, sj=sj)
+        _, prob = pair_score_fwd(Zc, H, batch, T, want_logit=False)
         # torch's BCE numerics (log clamped at -100, backward clamped at 1e-12) in one fused pass;
         # weights fold the means and the 1/m of main_disentangled.py:195
         loss, dS = link_bce(prob, labels, weights, want_grad=need_grad)
         if need_grad:
             dZ, dH = pair_score_bwd(Zc, H, batch, dS, T)
-            factor_bwd(graph, Zc, dH, kstar, w, s, beta, T, dZ=dZ)
+            factor_bwd(graph, Zc, dH, kstar, w, s, beta, T, dZ=dZ, sj=sj)
             ctx.save_for_backward(dZ)
         ctx.mark_non_differentiable(prob, H)
         return loss, prob, H

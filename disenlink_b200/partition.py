@@ -148,8 +148,8 @@ class CudaBackend:
     def edge_attn_fwd(self, g, Z, T, kstar, w, s):
         self.ops.edge_attn_fwd(g, Z, T, out=(kstar, w, s))
 
-    def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H):
-        self.ops.factor_spmm_fwd(g, Z, kstar, w, s, beta, out=H)
+    def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H, sj=None):
+        self.ops.factor_spmm_fwd(g, Z, kstar, w, s, beta, out=H, sj=sj)
 
     def pair_score_fwd(self, Z, H, shard, T, prob_slice):
         self.ops.pair_score_fwd(Z, H, shard, T, out=(None, prob_slice))
@@ -171,8 +171,8 @@ class CudaBackend:
     def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r):
         self.ops.factor_bwd_gather(g, Z, G, kstar, w, s, beta, dZ, r)
 
-    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ):
-        self.ops.factor_bwd_edges(g, Z, G, kstar, w, s, r, beta, T, dZ)
+    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ, sj=None):
+        self.ops.factor_bwd_edges(g, Z, G, kstar, w, s, r, beta, T, dZ, sj=sj)
 
 
 class PartitionedLinkStep:
@@ -204,6 +204,7 @@ class PartitionedLinkStep:
         nnz = self.graph.nnz
         self.kstar = torch.empty(max(nnz, 1), dtype=torch.uint8, device=dev)
         self.w = torch.empty(max(nnz, 1), **f32)
+        self.sj = torch.empty(max(nnz, 1), **f32)     # s[col, kstar] per local entry, forward -> backward pass 2
         self.s = torch.ones(part.n_pad, K, **f32)
         self.r = torch.zeros(part.n_pad, K, **f32)
         self.H = torch.zeros(part.n_pad, K, d, **f32)
@@ -222,7 +223,7 @@ class PartitionedLinkStep:
         mark("attn_fwd")
         all_gather_rows(self.s, part, self.group)
         mark("ag_s")
-        be.factor_spmm_fwd(g, Z, self.kstar, self.w, self.s, self.beta, self.H)
+        be.factor_spmm_fwd(g, Z, self.kstar, self.w, self.s, self.beta, self.H, self.sj)
         mark("spmm_fwd")
         all_gather_rows(self.H, part, self.group)
         mark("ag_H")
@@ -251,7 +252,7 @@ class PartitionedLinkStep:
         mark("bwd_gather")
         all_gather_rows(self.r, part, self.group)
         mark("ag_r")
-        be.factor_bwd_edges(g, Z, self.dH, self.kstar, self.w, self.s, self.r, self.beta, self.T, self.dZ)
+        be.factor_bwd_edges(g, Z, self.dH, self.kstar, self.w, self.s, self.r, self.beta, self.T, self.dZ, self.sj)
         mark("bwd_edges")
         return self.dZ
 

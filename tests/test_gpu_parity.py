@@ -267,6 +267,28 @@ def test_run_to_run_bitwise_determinism(dl):
     assert torch.equal(outs[0][1], outs[0][1][rev])
 
 
+@pytest.mark.parametrize("K,d", [(8, 16), (5, 32), (3, 7)])
+def test_saved_normaliser_sj(dl, K, d):
+    """dl_factor_spmm_fwd's optional sj_out is exactly s[col, kstar] per entry (streamed and
+    fallback paths), and handing it to the backward changes nothing, bit for bit."""
+    ops, Graph = dl
+    rng = np.random.default_rng(K * 100 + d)
+    n = 6000
+    src, dst = random_graph(rng, n, 50000, hubs=((2, 3000),))
+    Z = t((rng.standard_normal((n, K, d)) * 0.3).astype(np.float32))
+    G = t(rng.standard_normal((n, K, d)).astype(np.float32))
+    g = Graph.from_edges(t(src), t(dst), n)
+    kstar, w, s = ops.edge_attn_fwd(g, Z, 1.0)
+    sj = torch.full((g.nnz,), float("nan"), dtype=torch.float32, device=DEV)
+    H1 = ops.factor_spmm_fwd(g, Z, kstar, w, s, 0.5, sj=sj)
+    H0 = ops.factor_spmm_fwd(g, Z, kstar, w, s, 0.5)
+    assert torch.equal(H0, H1)
+    assert torch.equal(sj, s[g.col.long(), kstar.long()])
+    dZ0, r0 = ops.factor_bwd(g, Z, G, kstar, w, s, 0.5, 1.0)
+    dZ1, r1 = ops.factor_bwd(g, Z, G, kstar, w, s, 0.5, 1.0, sj=sj)
+    assert torch.equal(dZ0, dZ1) and torch.equal(r0, r1)
+
+
 def test_large_graph_properties(dl):
     """Size-independent properties at a size the dense reference cannot touch (N = 1M,
     nnz ~ 2*10^7): attention columns sum to one, kstar/w symmetric, scores symmetric in (u,v),

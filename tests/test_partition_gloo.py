@@ -58,7 +58,7 @@ class OracleBackend:
         w[:g.nnz] = torch.from_numpy(ww)
         s[g.part.lo:g.part.hi] = torch.from_numpy(ss[g.part.lo:g.part.hi])
 
-    def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H):
+    def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H, sj=None):
         out = self.o.factor_spmm_fwd(g.rowptr, g.col, Z.numpy(), kstar[:g.nnz].numpy(), w[:g.nnz].numpy(),
                                      s.numpy(), beta)
         H[g.part.lo:g.part.hi] = torch.from_numpy(out[g.part.lo:g.part.hi])
@@ -87,7 +87,7 @@ class OracleBackend:
         dZ[lo:hi] = torch.from_numpy(dz[lo:hi])
         r[lo:hi] = torch.from_numpy(rr[lo:hi])
 
-    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ):
+    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ, sj=None):
         lo, hi = g.part.lo, g.part.hi
         dz = dZ.numpy().copy()
         self.o.factor_bwd_edges(g.rowptr, g.col, Z.numpy(), G.numpy(), s.numpy(), r.numpy(), beta, T, dz)
