@@ -33,6 +33,8 @@ WORKLOADS = {
     # BASELINE.json configs[3] scale: snap-patents-sized synthetic
     "c4": dict(N=2_923_922, E=13_975_788, K=8, d=16, P=16_000_000, beta=0.5, T=1.0,
                name="snap-patents-scale synthetic 2.92M nodes / 13.98M directed edges, K=8, d=16"),
+    "c4k5": dict(N=2_923_922, E=13_975_788, K=5, d=32, P=16_000_000, beta=0.5, T=1.0,
+                 name="snap-patents-scale synthetic 2.92M nodes / 13.98M directed edges, K=5, d=32"),
     "mid": dict(N=5_000_000, E=50_000_000, K=8, d=16, P=10_000_000, beta=0.5, T=1.0,
                 name="synthetic power-law 5M nodes / 50M directed edges, K=8, d=16 (1/10 of c5)"),
     "tiny": dict(N=200_000, E=2_000_000, K=8, d=16, P=400_000, beta=0.5, T=1.0,

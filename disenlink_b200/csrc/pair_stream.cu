@@ -23,8 +23,10 @@ struct PairStreamCfg {
   static constexpr int STAGE_B = (DL_HS + PS_OWN) * 2 * ROWB;      // (Z, H) rows of 4 others + own slots
   static constexpr int BUDGET = 200 * 1024;
   static constexpr int NW_RAW = BUDGET / (PS_RING * STAGE_B);
-  static constexpr bool OK = NW_RAW >= 4 && M::EB == 4;
-  static constexpr int NW = NW_RAW >= 16 ? 16 : (NW_RAW >= 4 ? NW_RAW : 4);
+  static constexpr bool OK = NW_RAW >= 4 && M::EB == 4 && M::NP <= 4;   // NP = 5 spills badly: row-per-warp kernel
+  // shapes whose row needs several passes over the warp hold 2x the registers: fewer, fatter warps
+  static constexpr int NW_CAP = (M::NP >= 2) ? 8 : 16;
+  static constexpr int NW = NW_RAW >= NW_CAP ? NW_CAP : (NW_RAW >= 4 ? NW_RAW : 4);
   static constexpr int THREADS = NW * 32;
   static constexpr size_t SMEM = (size_t)NW * PS_RING * STAGE_B;
 };
