@@ -16,7 +16,8 @@
 // This replaces two launches (routing, row sums) and ~66 warp instructions per entry by one launch
 // and ~35.
 //
-// Instantiated for K <= 8, d in {4, 8, 16}; other shapes use attn_stream.cu.
+// Instantiated for K <= 8, d in {8, 16, 32} (the shapes of the reference's configs with K <= 8);
+// other shapes use attn_stream.cu.
 #include "dl_dispatch.cuh"
 #include "dl_stream.cuh"
 #include "dl_fl.cuh"
@@ -39,8 +40,9 @@ template <int K_, int d_>
 struct AflCfg {
   static constexpr int K = K_, d = d_, D = K_ * d_;
   static constexpr int LPE = 8, EPS = 32 / LPE, QPC = DL_CH / EPS, C4 = d_ / 4;
-  static constexpr bool SHAPE_OK = (K_ <= LPE) && (d_ % 4 == 0) && (C4 == 1 || C4 == 2 || C4 == 4) &&
-                                   (K_ * C4 <= 32);
+  static constexpr bool SHAPE_OK = (K_ <= LPE) && (d_ % 4 == 0) && (C4 == 1 || C4 == 2 || C4 == 4 || C4 == 8) &&
+                                   (K_ * C4 <= 64);
+  static constexpr int MAXW = (C4 == 8) ? (AFL_MAXW < 16 ? AFL_MAXW : 16) : AFL_MAXW;   // d = 32: 2x the registers
   static constexpr int ROWB = D * 4;
   static constexpr int ROWS = ((ROWB + 127) / 128) * 128;
   static constexpr int OWN_OFF = EPS * ROWS;
@@ -48,7 +50,7 @@ struct AflCfg {
   static constexpr int BUDGET = 226 * 1024;
   static constexpr int NW_RAW = BUDGET / (AFL_RING * STAGE_B);
   static constexpr bool OK = SHAPE_OK && NW_RAW >= 4;
-  static constexpr int NW = NW_RAW >= AFL_MAXW ? AFL_MAXW : (NW_RAW >= 4 ? NW_RAW : 4);
+  static constexpr int NW = NW_RAW >= MAXW ? MAXW : (NW_RAW >= 4 ? NW_RAW : 4);
   static constexpr int THREADS = NW * 32;
   static constexpr size_t SMEM = (size_t)NW * AFL_RING * STAGE_B;
   __device__ static __forceinline__ int key(int kap) { return (kap / (8 / C4)) & (C4 - 1); }
@@ -65,6 +67,9 @@ __device__ __forceinline__ float afl_dot(const float4 (&a)[C::C4], const float4 
   float p[C::C4];
 #pragma unroll
   for (int c = 0; c < C::C4; ++c) p[c] = dl_chunk_dot(a[c], b[c]);
+  if (C::C4 == 8)
+    return __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1 % C::C4]), __fadd_rn(p[2 % C::C4], p[3 % C::C4])),
+                     __fadd_rn(__fadd_rn(p[4 % C::C4], p[5 % C::C4]), __fadd_rn(p[6 % C::C4], p[7 % C::C4])));
   if (C::C4 == 4) return __fadd_rn(__fadd_rn(p[0], p[1]), __fadd_rn(p[2], p[3 % C::C4]));
   if (C::C4 == 2) return __fadd_rn(p[0], p[1 % C::C4]);
   return p[0];
@@ -90,6 +95,16 @@ k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __r
   const int pk = lane / C4, pc = lane % C4;
   const unsigned pdst = (unsigned)(pk * C4 + (pc ^ C::key(pk))) * 16u;
   const bool pact = lane < PIECES;
+  // rows of more than 32 pieces (D > 128): lane t also copies piece t + 32
+  const int pk2 = (lane + 32) / C4;
+  const unsigned pdst2 = (unsigned)(pk2 * C4 + (pc ^ C::key(pk2))) * 16u;
+  const bool pact2 = PIECES > 32 && lane + 32 < PIECES;
+  auto stage_row = [&](unsigned dst, const float* src) {
+    if (pact) fl_cp16(dst + pdst, src + lane * 4);
+    if (PIECES > 32) {
+      if (pact2) fl_cp16(dst + pdst2, src + (lane + 32) * 4);
+    }
+  };
   const unsigned myblk = (unsigned)(kap * C4 * 16) | ((unsigned)C::key(kap) << 4);
 
   DlChunkStream cs;
@@ -122,7 +137,7 @@ k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __r
 #pragma unroll
     for (int e = 0; e < EPS; ++e) {
       const long long cc = __shfl_sync(DL_FULL, m.col, q * EPS + e);
-      if (((vq >> e) & 1u) && pact) fl_cp16(st + e * ROWS + pdst, Z + cc * D + lane * 4);
+      if ((vq >> e) & 1u) stage_row(st + e * ROWS, Z + cc * D);
     }
     if ((m.nmask >> (q * EPS)) & ((1u << EPS) - 1u)) {
       unsigned starts = (m.smask >> (q * EPS)) & ((1u << EPS) - 1u);
@@ -131,7 +146,7 @@ k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __r
         const int pos = __ffs(starts) - 1;
         starts &= starts - 1;
         const long long node = g.row_base + __shfl_sync(DL_FULL, m.row, q * EPS + pos);
-        if (pact) fl_cp16(st + C::OWN_OFF + o * ROWS + pdst, Z + node * D + lane * 4);
+        stage_row(st + C::OWN_OFF + o * ROWS, Z + node * D);
         ++o;
       }
     }
@@ -303,6 +318,10 @@ int dl_launch_attn_fl(const DlGraphDev& g, const float* Z, int K, int d, float T
   if (K == 8 && d == 16) rc = AflLaunch<8, 16>::run(g, Z, T, kstar, w, s, scratch, st);
   else if (K == 8 && d == 8) rc = AflLaunch<8, 8>::run(g, Z, T, kstar, w, s, scratch, st);
   else if (K == 5 && d == 16) rc = AflLaunch<5, 16>::run(g, Z, T, kstar, w, s, scratch, st);
+  else if (K == 5 && d == 32) rc = AflLaunch<5, 32>::run(g, Z, T, kstar, w, s, scratch, st);
+  else if (K == 3 && d == 32) rc = AflLaunch<3, 32>::run(g, Z, T, kstar, w, s, scratch, st);
+  else if (K == 4 && d == 32) rc = AflLaunch<4, 32>::run(g, Z, T, kstar, w, s, scratch, st);
+  else if (K == 8 && d == 32) rc = AflLaunch<8, 32>::run(g, Z, T, kstar, w, s, scratch, st);
   if (rc != DL_OK) return rc;
   return dl_gather_chain_rowsum(g, K, scratch, s, st);
 }
