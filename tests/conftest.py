@@ -21,7 +21,15 @@ def golden_names(prefix=""):
 
 
 def load_golden(name):
-    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    """Fixture arrays; the big fixtures store ids as int32 and alias the loss positives to the
+    training edges (see make_golden.py COMPACT) -- both undone here."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    for k, v in list(g.items()):
+        if v.dtype == np.int32:
+            g[k] = v.astype(np.int64)
+    if "loss_neg_u" in g and "loss_pos_u" not in g:
+        g["loss_pos_u"], g["loss_pos_v"] = g["src"], g["dst"]
+    return g
 
 
 GRAPH_FIXTURES = [n for n in golden_names() if not n.startswith("module_")]
