@@ -129,8 +129,8 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
     const int ks = m.info;
 #ifndef FL_EXP_NOSR
     if (m.row >= 0) {
-      if (!sj) m.sj = __ldg(s + (long long)m.col * K + ks);
-      m.rj = __ldg(r + (long long)m.col * K + ks);
+      if (!sj) m.sj = fl_ldg_small(s + (long long)m.col * K + ks);
+      m.rj = fl_ldg_small(r + (long long)m.col * K + ks);
     }
 #endif
     const int up = __shfl_up_sync(DL_FULL, m.row, EPS);
@@ -167,7 +167,7 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
 #else
       if (false)
 #endif
-        fl_cp16(st + C::SL_OFF + grp * C::SLB + kap * 16, G + cc * D + kk * d + kap * 4);
+        fl_cp16_small(st + C::SL_OFF + grp * C::SLB + kap * 16, G + cc * D + kk * d + kap * 4);
     }
     if ((m.nmask >> (q * EPS)) & ((1u << EPS) - 1u)) {
       unsigned starts = (m.smask >> (q * EPS)) & ((1u << EPS) - 1u);

@@ -30,3 +30,17 @@ __device__ __forceinline__ void fl_cp4(unsigned dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
+
+// small gathers (a 64-byte routed slice, a 4-byte per-node scalar): optional L2 prefetch-size
+// qualifier, set per build for experiments (-DFL_SMALL_L2='".L2::64B"')
+#ifndef FL_SMALL_L2
+#define FL_SMALL_L2 ""
+#endif
+__device__ __forceinline__ void fl_cp16_small(unsigned dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global" FL_SMALL_L2 " [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float fl_ldg_small(const float* p) {
+  float v;
+  asm volatile("ld.global.nc" FL_SMALL_L2 ".f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}

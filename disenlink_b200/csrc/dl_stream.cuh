@@ -75,8 +75,11 @@ __device__ __forceinline__ void dl_bulk_g2s(void* smem_dst, const void* gmem_src
 }
 
 // 16-byte cp.async global -> shared (LDGSTS), L2-only (.cg): gathered rows are not reused via L1
+#ifndef DL_CPA_L2
+#define DL_CPA_L2 ""          // optional L2 prefetch-size qualifier for experiments, e.g. ".L2::64B"
+#endif
 __device__ __forceinline__ void dl_cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dl_smem_u32(smem_dst)), "l"(gmem_src)
+  asm volatile("cp.async.cg.shared.global" DL_CPA_L2 " [%0], [%1], 16;" ::"r"(dl_smem_u32(smem_dst)), "l"(gmem_src)
                : "memory");
 }
 __device__ __forceinline__ void dl_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }

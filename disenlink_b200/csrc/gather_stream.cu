@@ -22,12 +22,27 @@
 // A row cut by a range boundary leaves its partial sums in a carry buffer (head / tail per range);
 // k_gather_chain sums the pieces of such rows in range order and applies the row epilogue, and
 // k_gather_empty_rows writes the rows that have no entries.  No atomics anywhere.
+// the gathers of this file are 64-byte slices and 4-byte scalars: ask L2 not to fetch beyond 64 B
+// (measured: .L2::64B -2 %, .L2::256B +5 % against no qualifier)
+#ifndef DL_CPA_L2
+#define DL_CPA_L2 ".L2::64B"
+#endif
+#ifndef DL_LDG_L2
+#define DL_LDG_L2 ".L2::64B"
+#endif
 #include "dl_dispatch.cuh"
 #include "dl_stream.cuh"
 
 namespace {
 
 constexpr int GS_WARPS = 16;   // warps per CTA
+
+// the 4-byte s[col,k] gather, with the L2 prefetch-size qualifier of this file
+__device__ __forceinline__ float gs_ldg_s(const float* p) {
+  float v;
+  asm volatile("ld.global.nc" DL_LDG_L2 ".f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 
 // flat width of a row's accumulator / carry record
 __host__ __device__ constexpr int carry_width(int mode, int K, int d) {
@@ -290,7 +305,7 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
   long long cn = cs.next(c);
   load_meta(cn, mB);
   float sjA = 1.0f, sjB = 1.0f;
-  if (MODE == 0 && mA.ks != 255) sjA = __ldg(s + (long long)mA.col * K + mA.ks);
+  if (MODE == 0 && mA.ks != 255) sjA = gs_ldg_s(s + (long long)mA.col * K + mA.ks);
   int buf = 0;
   issue_slices(tile, mA);
   dl_cp_async_commit();
@@ -299,7 +314,7 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
     // pipeline: metadata two chunks ahead, s gather + slices one chunk ahead
     const long long cnn = cs.next(cn);
     load_meta(cnn, mC);
-    if (MODE == 0 && mB.ks != 255) sjB = __ldg(s + (long long)mB.col * K + mB.ks);
+    if (MODE == 0 && mB.ks != 255) sjB = gs_ldg_s(s + (long long)mB.col * K + mB.ks);
     issue_slices(tile + (buf ^ 1) * TILE_B, mB);
     dl_cp_async_commit();
     dl_cp_async_wait<1>();
