@@ -88,8 +88,8 @@ template <int K_, int d_>
 __global__ void __launch_bounds__(FlCfg<K_, d_>::THREADS, 1)
 k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restrict__ G,
                const unsigned char* __restrict__ kstar, const float* __restrict__ s,
-               const float* __restrict__ r, const float* __restrict__ sj, float omb, float T,
-               float* __restrict__ dZ, float* __restrict__ carry) {
+               const float* __restrict__ r, const float* __restrict__ sj, const float2* __restrict__ sr,
+               float omb, float T, float* __restrict__ dZ, float* __restrict__ carry) {
   using C = FlCfg<K_, d_>;
   constexpr int K = C::K, d = C::d, D = C::D, LPE = C::LPE, EPS = C::EPS, QPC = C::QPC, C4 = C::C4;
   constexpr int ROWS = C::ROWS, STAGE_B = C::STAGE_B, OWN_B = C::OWN_B;
@@ -129,8 +129,14 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
     const int ks = m.info;
 #ifndef FL_EXP_NOSR
     if (m.row >= 0) {
-      if (!sj) m.sj = fl_ldg_small(s + (long long)m.col * K + ks);
-      m.rj = fl_ldg_small(r + (long long)m.col * K + ks);
+      if (sr) {                 // (s, r) interleaved per (node, factor): one 8-byte gather for both
+        const float2 v = __ldg(sr + (long long)m.col * K + ks);
+        if (!sj) m.sj = v.x;
+        m.rj = v.y;
+      } else {
+        if (!sj) m.sj = fl_ldg_small(s + (long long)m.col * K + ks);
+        m.rj = fl_ldg_small(r + (long long)m.col * K + ks);
+      }
     }
 #endif
     const int up = __shfl_up_sync(DL_FULL, m.row, EPS);
@@ -372,8 +378,8 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
 template <int K_, int d_>
 struct FlLaunch {
   static int run(const DlGraphDev& g, const float* Z, const float* G, const unsigned char* kstar,
-                 const float* s, const float* r, const float* sj, float omb, float T, float* dZ, float* carry,
-                 cudaStream_t st) {
+                 const float* s, const float* r, const float* sj, const float2* sr, float omb, float T, float* dZ,
+                 float* carry, cudaStream_t st) {
     using C = FlCfg<K_, d_>;
     int dev = 0, sms = 0;
     DL_CUDA_TRY(cudaGetDevice(&dev));
@@ -385,7 +391,7 @@ struct FlLaunch {
     long long grid = (n_ranges + C::NW - 1) / C::NW;
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
-    k_bwd_edges_fl<K_, d_><<<(int)grid, C::THREADS, C::SMEM, st>>>(g, Z, G, kstar, s, r, sj, omb, T, dZ, carry);
+    k_bwd_edges_fl<K_, d_><<<(int)grid, C::THREADS, C::SMEM, st>>>(g, Z, G, kstar, s, r, sj, sr, omb, T, dZ, carry);
     DL_LAUNCH_CHECK();
     return DL_OK;
   }
@@ -394,14 +400,34 @@ struct FlLaunch {
 }  // namespace
 
 // returns -1000 when (K, d) has no factor-per-lane instantiation; scratch as for bwd_stream.cu
+namespace {
+// sr[node,k] = (s[node,k], r[node,k]): a streaming pass of 16 bytes per (node, factor) that turns the two
+// per-entry 4-byte gathers of pass 2 into one 8-byte gather
+__global__ void k_pack_sr(const float* __restrict__ s, const float* __restrict__ r, long long n, float2* __restrict__ sr) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+    sr[t] = make_float2(__ldg(s + t), __ldg(r + t));
+}
+}  // namespace
+
+bool dl_bwd_edges_fl_has(int K, int d) {
+  return (K == 8 && d == 16) || (K == 8 && d == 8) || (K == 5 && d == 16);
+}
+
 int dl_launch_bwd_edges_fl(const DlGraphDev& g, const float* Z, const float* G, const unsigned char* kstar,
-                           const float* s, const float* r, const float* sj, int K, int d, float omb, float T,
-                           float* dZ, float* scratch, cudaStream_t st) {
-  if (!g.erow || g.nnz == 0 || !scratch) return -1000;
+                           const float* s, const float* r, const float* sj, float* sr_scratch, long long n_nodes,
+                           int K, int d, float omb, float T, float* dZ, float* scratch, cudaStream_t st) {
+  if (!g.erow || g.nnz == 0 || !scratch || !dl_bwd_edges_fl_has(K, d)) return -1000;
+  const float2* sr = nullptr;
+  if (sr_scratch && n_nodes > 0) {
+    k_pack_sr<<<148 * 8, 256, 0, st>>>(s, r, n_nodes * K, reinterpret_cast<float2*>(sr_scratch));
+    DL_LAUNCH_CHECK();
+    sr = reinterpret_cast<const float2*>(sr_scratch);
+  }
   int rc = -1000;
-  if (K == 8 && d == 16) rc = FlLaunch<8, 16>::run(g, Z, G, kstar, s, r, sj, omb, T, dZ, scratch, st);
-  else if (K == 8 && d == 8) rc = FlLaunch<8, 8>::run(g, Z, G, kstar, s, r, sj, omb, T, dZ, scratch, st);
-  else if (K == 5 && d == 16) rc = FlLaunch<5, 16>::run(g, Z, G, kstar, s, r, sj, omb, T, dZ, scratch, st);
+  if (K == 8 && d == 16) rc = FlLaunch<8, 16>::run(g, Z, G, kstar, s, r, sj, sr, omb, T, dZ, scratch, st);
+  else if (K == 8 && d == 8) rc = FlLaunch<8, 8>::run(g, Z, G, kstar, s, r, sj, sr, omb, T, dZ, scratch, st);
+  else if (K == 5 && d == 16) rc = FlLaunch<5, 16>::run(g, Z, G, kstar, s, r, sj, sr, omb, T, dZ, scratch, st);
   if (rc != DL_OK) return rc;
   return dl_gather_chain_add(g, K, d, scratch, dZ, st);
 }

@@ -131,8 +131,8 @@ int dl_launch_pair_bwd_stream(const DlGraphDev& g, const int* inc_pair, const fl
 
 // Factor-per-lane backward pass 2 (bwd_fl.cu).  Returns -1000 when (K, d) has no instantiation.
 int dl_launch_bwd_edges_fl(const DlGraphDev& g, const float* Z, const float* G, const unsigned char* kstar,
-                           const float* s, const float* r, const float* sj, int K, int d, float omb, float T,
-                           float* dZ, float* scratch, cudaStream_t st);
+                           const float* s, const float* r, const float* sj, float* sr_scratch, long long n_nodes,
+                           int K, int d, float omb, float T, float* dZ, float* scratch, cudaStream_t st);
 
 // Factor-per-lane attention + row sums (attn_fl.cu).  Returns -1000 when (K, d) has no instantiation.
 int dl_gather_chain_rowsum(const DlGraphDev& g, int K, float* scratch, float* s_out, cudaStream_t st);

@@ -424,8 +424,8 @@ int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
 
 int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
                         const uint8_t* kstar, const float* w, const float* s, const float* r,
-                        const float* sj, int K, int d, float one_minus_beta, float T, float* dZ,
-                        float* hub_ws, dl_stream_t stream) {
+                        const float* sj, float* sr_scratch, int64_t n_nodes, int K, int d,
+                        float one_minus_beta, float T, float* dZ, float* hub_ws, dl_stream_t stream) {
   if (!dl_graph_ok(g_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
   if (g_host->N == 0) return DL_OK;
   if (!Z || !G || !s || !dZ || !r || (g_host->nnz > 0 && !kstar)) return DL_EINVAL;
@@ -442,10 +442,13 @@ int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
     rc = dl_launch_bwd_edges_split(g, Z, G, kstar, w, s, r, K, d, one_minus_beta, T, dZ, hub_ws, st);
   if (rc == DL_OK) return DL_OK;
   if (rc != -1000) return rc;
-  // factor-per-lane kernel (bwd_fl.cu) for the K <= 8, d <= 16 shape class; DL_NO_FL=1 disables it
+  // factor-per-lane kernel (bwd_fl.cu) for the K <= 8, d <= 16 shape class; DL_NO_FL=1 disables it.
+  // The interleaved (s, r) gather is opt-in (DL_USE_SR=1): -3.5 % at C5, +3 % at 1/10 of it, both
+  // inside the clock wander of a power-capped run
   if (!getenv("DL_NO_STREAM") && !getenv("DL_NO_FL"))
-    rc = dl_launch_bwd_edges_fl(g, Z, G, kstar, s, r, getenv("DL_NO_SJ") ? nullptr : sj, K, d, one_minus_beta, T, dZ,
-                                hub_ws, st);
+    rc = dl_launch_bwd_edges_fl(g, Z, G, kstar, s, r, getenv("DL_NO_SJ") ? nullptr : sj,
+                                getenv("DL_USE_SR") ? sr_scratch : nullptr, n_nodes, K, d, one_minus_beta, T, dZ, hub_ws,
+                                st);
   if (rc == DL_OK) return DL_OK;
   if (rc != -1000) return rc;
   if (!getenv("DL_NO_STREAM"))
@@ -473,13 +476,15 @@ int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
 }
 
 int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const uint8_t* kstar,
-                  const float* w, const float* s, const float* sj, int K, int d, float beta,
-                  float one_minus_beta, float T, float* dZ, float* r, float* hub_ws, dl_stream_t stream) {
+                  const float* w, const float* s, const float* sj, float* sr_scratch, int64_t n_nodes, int K,
+                  int d, float beta, float one_minus_beta, float T, float* dZ, float* r, float* hub_ws,
+                  dl_stream_t stream) {
   if (!(T == T) || T == 0.0f) return DL_EINVAL;
   int rc = dl_factor_bwd_gather(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, hub_ws,
                                 stream);
   if (rc) return rc;
-  return dl_factor_bwd_edges(g_host, Z, G, kstar, w, s, r, sj, K, d, one_minus_beta, T, dZ, hub_ws, stream);
+  return dl_factor_bwd_edges(g_host, Z, G, kstar, w, s, r, sj, sr_scratch, n_nodes, K, d, one_minus_beta, T, dZ,
+                             hub_ws, stream);
 }
 
 }  // extern "C"

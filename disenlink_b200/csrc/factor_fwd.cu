@@ -308,6 +308,23 @@ inline int fixup_blocks(long long n) {
 
 }  // namespace
 
+// Zs[i,k,:] = Z[i,k,:] / s[i,k]: one streaming pass (8*N*D bytes at full bandwidth) that takes the
+// s[col,k] gather -- one of the two DRAM transactions per entry -- out of the aggregation kernel
+static __global__ void k_scale_rows(const float* __restrict__ Z, const float* __restrict__ s, long long n_rows,
+                                    int K, int d, float* __restrict__ Zs) {
+  const long long D4 = (long long)K * d / 4, total = n_rows * D4;
+  const int d4 = d / 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long long row = t / D4;
+    const int k = (int)((t - row * D4) / d4);
+    const float sk = __ldg(s + row * K + k);
+    float4 v = __ldg(reinterpret_cast<const float4*>(Z) + t);
+    v.x = __fdiv_rn(v.x, sk); v.y = __fdiv_rn(v.y, sk); v.z = __fdiv_rn(v.z, sk); v.w = __fdiv_rn(v.w, sk);
+    reinterpret_cast<float4*>(Zs)[t] = v;
+  }
+}
+
 // per-entry copy of s[col, kstar] (sj_out) for the paths that do not write it on the way
 static __global__ void k_entry_sj(DlGraphDev g, const unsigned char* __restrict__ kstar, const float* __restrict__ s,
                            int K, float* __restrict__ sj) {
@@ -377,7 +394,8 @@ int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float
 
 int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
                        const float* w, const float* s, int K, int d, float beta,
-                       float one_minus_beta, float* H, float* sj_out, float* hub_ws, dl_stream_t stream) {
+                       float one_minus_beta, float* H, float* sj_out, float* zs_scratch, float* hub_ws,
+                       dl_stream_t stream) {
   if (!dl_graph_ok(g_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
   if (g_host->N == 0) return DL_OK;
   if (!Z || !s || !H || (g_host->nnz > 0 && (!kstar || !w))) return DL_EINVAL;
@@ -386,6 +404,16 @@ int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* ks
   const DlGraphDev g = dl_graph_dev(g_host);
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
+  // pre-scaled path: needs every gathered row inside [0, N) (a graph that is not row-partitioned)
+  if (zs_scratch && (sj_out || g.row_base != 0)) return DL_EINVAL;
+  if (zs_scratch && g.nnz > 0 && d % 4 == 0 && g.erow && !getenv("DL_NO_STREAM") && !getenv("DL_NO_PRESCALE")) {
+    k_scale_rows<<<148 * 8, 256, 0, st>>>(Z, s, g.N, K, d, zs_scratch);
+    DL_LAUNCH_CHECK();
+    rc = dl_launch_gather_stream(0, g, Z, zs_scratch, kstar, w, nullptr, K, d, beta, one_minus_beta, H, nullptr,
+                                 hub_ws, st);
+    if (rc == DL_OK) return DL_OK;
+    if (rc != -1000) return rc;                // -1000: no streaming instantiation, the scratch goes unused
+  }
   if (!getenv("DL_NO_STREAM"))
     rc = dl_launch_gather_stream(0, g, Z, Z, kstar, w, s, K, d, beta, one_minus_beta, H, sj_out, hub_ws, st);
   if (rc == DL_OK) return DL_OK;             // carries, chained rows and empty rows all handled

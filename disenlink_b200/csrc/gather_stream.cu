@@ -148,7 +148,8 @@ template <class M, int MODE>
 struct GatherStreamCfg {
   static constexpr int SLB = M::d * 4;                                  // bytes of one routed slice
   static constexpr int TILE_B = (MODE == 2) ? 0 : DL_CH * SLB;          // one chunk of slices
-  static constexpr size_t SMEM = (size_t)GS_WARPS * 2 * TILE_B;
+  static constexpr int CF_B = (MODE == 2) ? 0 : DL_CH * 4;              // the chunk's coefficients
+  static constexpr size_t SMEM = (size_t)GS_WARPS * (2 * TILE_B + CF_B);
 };
 
 template <class M, int MODE>
@@ -163,7 +164,8 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
   constexpr int W = (MODE == 2) ? K : D;
   extern __shared__ __align__(128) unsigned char dl_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* tile = dl_smem_raw + (size_t)warp * 2 * TILE_B;
+  unsigned char* tile = dl_smem_raw + (size_t)warp * (2 * TILE_B + C::CF_B);
+  float* cfbuf = reinterpret_cast<float*>(tile + 2 * TILE_B);
   const long long gw = (long long)blockIdx.x * GS_WARPS + warp;
   const int grp = lane / LP, gg = lane % LP, slot = M::slot(lane);
   const bool glane = gg < L;
@@ -299,22 +301,64 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
     for (int p = 0; p < NP; ++p) acc[p] = dl_zero4();
   };
 
+  // L2 prefetch of the row vectors the epilogue of a row needs, one chunk before the row starts
+  auto prefetch_starts = [&](const Meta& m, int last_row_before) {
+#ifdef GS_EXP_PREFETCH
+    if (MODE == 2) return;
+    const int prev = __shfl_up_sync(DL_FULL, m.row, 1);
+    const bool start = m.row >= 0 && m.row != (lane == 0 ? last_row_before : prev);
+    if (start) {
+      const long long node = g.row_base + m.row;
+      const char* zp = reinterpret_cast<const char*>(Z + node * D);
+#pragma unroll
+      for (int l = 0; l < D * 4; l += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(zp + l));
+      if (MODE == 1) {
+        const char* gp = reinterpret_cast<const char*>(SRC + node * D);
+        const char* dp = reinterpret_cast<const char*>(OUT + node * D);
+#pragma unroll
+        for (int l = 0; l < D * 4; l += 128) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + l));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(dp + l));
+        }
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(s + node * K)));
+      }
+    }
+#endif
+  };
+
   long long c = cs.first(gw);
   Meta mA, mB, mC;
   load_meta(c, mA);
   long long cn = cs.next(c);
   load_meta(cn, mB);
   float sjA = 1.0f, sjB = 1.0f;
-  if (MODE == 0 && mA.ks != 255) sjA = gs_ldg_s(s + (long long)mA.col * K + mA.ks);
+  // s == nullptr in MODE 0: SRC holds slices already divided by s (factor_fwd.cu k_scale_rows)
+  if (MODE == 0 && s != nullptr && mA.ks != 255) sjA = gs_ldg_s(s + (long long)mA.col * K + mA.ks);
+#ifdef GS_EXP_SJLEAD
+  Meta mD;
+  long long cnn = cs.next(cn);
+  load_meta(cnn, mC);
+  float sjC = 1.0f;
+  if (MODE == 0 && s != nullptr && mB.ks != 255) sjB = gs_ldg_s(s + (long long)mB.col * K + mB.ks);
+#endif
   int buf = 0;
+  prefetch_starts(mA, -1);
   issue_slices(tile, mA);
   dl_cp_async_commit();
 
   while (c >= 0) {
+#ifdef GS_EXP_SJLEAD
+    // ids three chunks ahead, the s gather two chunks ahead, slices one chunk ahead
+    const long long cnnn = cs.next(cnn);
+    load_meta(cnnn, mD);
+    if (MODE == 0 && s != nullptr && mC.ks != 255) sjC = gs_ldg_s(s + (long long)mC.col * K + mC.ks);
+#else
     // pipeline: metadata two chunks ahead, s gather + slices one chunk ahead
     const long long cnn = cs.next(cn);
     load_meta(cnn, mC);
-    if (MODE == 0 && mB.ks != 255) sjB = gs_ldg_s(s + (long long)mB.col * K + mB.ks);
+    if (MODE == 0 && s != nullptr && mB.ks != 255) sjB = gs_ldg_s(s + (long long)mB.col * K + mB.ks);
+#endif
+    prefetch_starts(mB, __shfl_sync(DL_FULL, mA.row, 31));
     issue_slices(tile + (buf ^ 1) * TILE_B, mB);
     dl_cp_async_commit();
     dl_cp_async_wait<1>();
@@ -333,7 +377,7 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
 
     // MODE 0 has no r output: the pointer carries the optional per-entry copy of s[col, kstar]
     // (sj_out of dl_factor_spmm_fwd) that lets backward pass 2 skip this gather
-    if (MODE == 0 && r != nullptr && mA.row >= 0) r[c * DL_CH + lane] = sjA;
+    if (MODE == 0 && r != nullptr && s != nullptr && mA.row >= 0) r[c * DL_CH + lane] = sjA;
     const float coefA = (MODE == 0) ? __fdiv_rn(mA.wv, sjA) : mA.wv;
     const unsigned vmask = __ballot_sync(DL_FULL, mA.row >= 0);
     const int cnt = __popc(vmask);
@@ -344,39 +388,70 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
     const bool st = mA.row >= 0 && (lane == 0 ? mA.row != cur_row : mA.row != prow);
     const unsigned starts = __ballot_sync(DL_FULL, st);
     int idx = 0;
-    while (idx < cnt) {
-      if ((starts >> idx) & 1u) {
-        flush(false);
-        cur_row = __shfl_sync(DL_FULL, mA.row, idx);
-        prefetch_row(cur_row);
-      }
-      const unsigned rest = (idx < 31) ? (starts & ~((2u << idx) - 1u)) : 0u;
-      const int end = rest ? (__ffs(rest) - 1) : cnt;
-      for (; idx < end; ++idx) {
-        const unsigned ke = (unsigned)__shfl_sync(DL_FULL, mA.ks, idx);
-        const float cf = __shfl_sync(DL_FULL, coefA, idx);
-        if (MODE == 2) {
+    if (MODE == 2) {
+      while (idx < cnt) {
+        if ((starts >> idx) & 1u) {
+          flush(false);
+          cur_row = __shfl_sync(DL_FULL, mA.row, idx);
+        }
+        const unsigned rest = (idx < 31) ? (starts & ~((2u << idx) - 1u)) : 0u;
+        const int end = rest ? (__ffs(rest) - 1) : cnt;
+        for (; idx < end; ++idx) {
+          const unsigned ke = (unsigned)__shfl_sync(DL_FULL, mA.ks, idx);
+          const float cf = __shfl_sync(DL_FULL, coefA, idx);
           if ((unsigned)lane == ke) acc2 = __fadd_rn(acc2, cf);
-        } else {
-          if (glane && (ke & (FPP - 1)) == (unsigned)slot) {
-            const float4 v = dl_lds4(sl + idx * SLB + gg * 16);
-            if (NP == 1) {
-              dl_fma4(acc[0], cf, v);
-            } else {
-              const unsigned pe = ke / FPP;
+        }
+      }
+    } else {
+      // Every lane group walks only the entries routed to ITS factor: mine[p] has bit i set when
+      // entry i of the chunk belongs to factor p*FPP + slot.  The walk is divergent between lane
+      // groups (no shuffles inside: coefficients and slices come from shared memory) and costs
+      // max-over-factors entries per run instead of all of them; each accumulator still receives
+      // its entries in CSR order, so the sums are bit-identical to an entry-by-entry walk.
+      cfbuf[lane] = coefA;
+      unsigned mine[NP];
 #pragma unroll
-              for (int p = 0; p < NP; ++p)
-                if (pe == (unsigned)p) dl_fma4(acc[p], cf, v);
-            }
+      for (int p = 0; p < NP; ++p) mine[p] = 0u;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const unsigned b = __ballot_sync(DL_FULL, mA.ks == k);
+        if (glane && slot == (k % FPP)) mine[k / FPP] = b;
+      }
+      __syncwarp();
+      while (idx < cnt) {
+        if ((starts >> idx) & 1u) {
+          flush(false);
+          cur_row = __shfl_sync(DL_FULL, mA.row, idx);
+          prefetch_row(cur_row);
+        }
+        const unsigned rest = (idx < 31) ? (starts & ~((2u << idx) - 1u)) : 0u;
+        const int end = rest ? (__ffs(rest) - 1) : cnt;
+        const unsigned runbits = ((end < 32) ? ((1u << end) - 1u) : 0xffffffffu) & ~((1u << idx) - 1u);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          unsigned m = mine[p] & runbits;
+          while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1;
+            const float cf = cfbuf[i];
+            const float4 v = dl_lds4(sl + i * SLB + gg * 16);
+            dl_fma4(acc[p], cf, v);
           }
         }
+        idx = end;
       }
     }
     __syncwarp();
     buf ^= 1;
+#ifdef GS_EXP_SJLEAD
+    c = cn; cn = cnn; cnn = cnnn;
+    mA = mB; mB = mC; mC = mD;
+    sjA = sjB; sjB = sjC;
+#else
     c = cn; cn = cnn;
     mA = mB; mB = mC;
     sjA = sjB;
+#endif
   }
   if (cur_range >= 0) flush(true);
   dl_cp_async_wait<0>();

@@ -60,16 +60,20 @@ def _optr(t):
     return ptr(t) if t is not None else None
 
 
-def factor_spmm_fwd(graph: Graph, Z, kstar, w, s, beta: float, out=None, sj=None):
+def factor_spmm_fwd(graph: Graph, Z, kstar, w, s, beta: float, out=None, sj=None, zs=None):
     """-> H [N,K,d].  [ref: model.py:75]  `sj` = optional f32 [nnz] buffer that receives s[col, kstar]
-    per entry (pass it on to factor_bwd / factor_bwd_edges)."""
+    per entry (pass it on to factor_bwd / factor_bwd_edges).  `zs` = optional [N,K,d] scratch: the
+    kernel then gathers slices pre-divided by s (one DRAM transaction per entry instead of two); only
+    for graphs that are not row-partitioned, and exclusive with `sj`."""
+    if zs is not None and (sj is not None or graph.row_base != 0 or graph.n_global != graph.N):
+        raise ValueError("zs needs a graph that is not row-partitioned and excludes sj")
     K, d = _check_Z(Z, graph.n_global)
     Z = Z.contiguous()
     dev = Z.device
     with torch.cuda.device(dev):
         H = torch.empty_like(Z) if out is None else out
         check(lib().dl_factor_spmm_fwd(graph.ref, ptr(Z), ptr(kstar), ptr(w), ptr(s), K, d,
-                                       float(beta), one_minus(beta), ptr(H), _optr(sj),
+                                       float(beta), one_minus(beta), ptr(H), _optr(sj), _optr(zs),
                                        ptr(graph.hub_scratch(K * d)), stream_of(dev)),
               "dl_factor_spmm_fwd")
     return H
@@ -86,12 +90,22 @@ def factor_bwd_gather(graph: Graph, Z, G, kstar, w, s, beta: float, dZ, r):
               "dl_factor_bwd_gather")
 
 
+def _sr_scratch(graph: Graph, s):
+    """[n, K, 2] scratch in which pass 2 interleaves (s, r) -- cached on the graph handle."""
+    buf = getattr(graph, "_sr_scratch", None)
+    if buf is None or buf.shape[0] != s.shape[0] or buf.shape[1] != s.shape[1] or buf.device != s.device:
+        buf = torch.empty(s.shape[0], s.shape[1], 2, dtype=torch.float32, device=s.device)
+        graph._sr_scratch = buf
+    return buf
+
+
 def factor_bwd_edges(graph: Graph, Z, G, kstar, w, s, r, beta: float, T: float, dZ, sj=None):
     """Pass 2 of the backward: dZ += attention-weight terms (needs r of every neighbour)."""
     K, d = _check_Z(Z, graph.n_global)
     dev = Z.device
     with torch.cuda.device(dev):
-        check(lib().dl_factor_bwd_edges(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), ptr(r), _optr(sj), K, d,
+        check(lib().dl_factor_bwd_edges(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), ptr(r), _optr(sj),
+                                        ptr(_sr_scratch(graph, s)), int(s.shape[0]), K, d,
                                         one_minus(beta), float(T), ptr(dZ),
                                         ptr(graph.hub_scratch(K * d)), stream_of(dev)),
               "dl_factor_bwd_edges")
@@ -109,7 +123,8 @@ def factor_bwd(graph: Graph, Z, G, kstar, w, s, beta: float, T: float = 1.0, dZ=
             dZ = torch.zeros_like(Z)
         if r is None:
             r = torch.empty(graph.n_global, K, dtype=torch.float32, device=dev)
-        check(lib().dl_factor_bwd(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), _optr(sj), K, d,
+        check(lib().dl_factor_bwd(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), _optr(sj),
+                                  ptr(_sr_scratch(graph, s)), int(s.shape[0]), K, d,
                                   float(beta), one_minus(beta), float(T), ptr(dZ), ptr(r),
                                   ptr(graph.hub_scratch(K * d)), stream_of(dev)), "dl_factor_bwd")
     return dZ, r
@@ -199,13 +214,25 @@ def pair_score_bwd(Z, H, batch: PairBatch, dS, T: float = 1.0, out=None):
 # --------------------------------------------------------------------------------------------
 # autograd Functions
 # --------------------------------------------------------------------------------------------
+def _spmm_side_buffers(graph: Graph, Z, need_grad: bool):
+    """-> (sj, zs) for factor_spmm_fwd.  A graph that is not row-partitioned gets the pre-scaled path
+    (zs: a transient [N,K,d] scratch; halves the DRAM transactions of the aggregation); a partitioned
+    one keeps s[col,kstar] per entry for the backward instead (sj)."""
+    if graph.row_base == 0 and graph.n_global == graph.N and graph.nnz > 0:
+        return None, torch.empty_like(Z)
+    if need_grad:
+        return torch.empty(max(graph.nnz, 1), dtype=torch.float32, device=Z.device), None
+    return None, None
+
+
 class _FactorAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Z, graph, beta, T):
         Zc = Z.contiguous()
         kstar, w, s = edge_attn_fwd(graph, Zc, T)
-        sj = torch.empty(max(graph.nnz, 1), dtype=torch.float32, device=Zc.device) if Z.requires_grad else None
-        H = factor_spmm_fwd(graph, Zc, kstar, w, s, beta, sj=sj)
+        sj, zs = _spmm_side_buffers(graph, Zc, Z.requires_grad)
+        H = factor_spmm_fwd(graph, Zc, kstar, w, s, beta, sj=sj, zs=zs)
+        del zs
         ctx.graph, ctx.beta, ctx.T, ctx.sj = graph, float(beta), float(T), sj
         ctx.save_for_backward(Zc, kstar, w, s)
         ctx.mark_non_differentiable(kstar, w, s)
@@ -343,8 +370,9 @@ class _LinkBCELoss(torch.autograd.Function):
         Zc = Z.detach().contiguous()
         need_grad = ctx.needs_input_grad[0]
         kstar, w, s = edge_attn_fwd(graph, Zc, T)
-        sj = torch.empty(max(graph.nnz, 1), dtype=torch.float32, device=Zc.device) if need_grad else None
-        H = factor_spmm_fwd(graph, Zc, kstar, w, s, beta, sj=sj)
+        sj, zs = _spmm_side_buffers(graph, Zc, need_grad)
+        H = factor_spmm_fwd(graph, Zc, kstar, w, s, beta, sj=sj, zs=zs)
+        del zs
         _, prob = pair_score_fwd(Zc, H, batch, T, want_logit=False)
         # torch's BCE numerics (log clamped at -100, backward clamped at 1e-12) in one fused pass;
         # weights fold the means and the 1/m of main_disentangled.py:195

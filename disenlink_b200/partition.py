@@ -23,6 +23,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -148,8 +150,8 @@ class CudaBackend:
     def edge_attn_fwd(self, g, Z, T, kstar, w, s):
         self.ops.edge_attn_fwd(g, Z, T, out=(kstar, w, s))
 
-    def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H, sj=None):
-        self.ops.factor_spmm_fwd(g, Z, kstar, w, s, beta, out=H, sj=sj)
+    def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H, sj=None, zs=None):
+        self.ops.factor_spmm_fwd(g, Z, kstar, w, s, beta, out=H, sj=sj, zs=zs)
 
     def pair_score_fwd(self, Z, H, shard, T, prob_slice):
         self.ops.pair_score_fwd(Z, H, shard, T, out=(None, prob_slice))
@@ -204,7 +206,10 @@ class PartitionedLinkStep:
         nnz = self.graph.nnz
         self.kstar = torch.empty(max(nnz, 1), dtype=torch.uint8, device=dev)
         self.w = torch.empty(max(nnz, 1), **f32)
-        self.sj = torch.empty(max(nnz, 1), **f32)     # s[col, kstar] per local entry, forward -> backward pass 2
+        # one rank: the aggregation gathers slices pre-divided by s (scratch = the dH buffer, idle
+        # during the forward); several ranks: s[col, kstar] per local entry goes forward -> pass 2
+        self.prescale = (part.world == 1) and not os.environ.get("DL_NO_PRESCALE")
+        self.sj = None if self.prescale else torch.empty(max(nnz, 1), **f32)
         self.s = torch.ones(part.n_pad, K, **f32)
         self.r = torch.zeros(part.n_pad, K, **f32)
         self.H = torch.zeros(part.n_pad, K, d, **f32)
@@ -223,7 +228,8 @@ class PartitionedLinkStep:
         mark("attn_fwd")
         all_gather_rows(self.s, part, self.group)
         mark("ag_s")
-        be.factor_spmm_fwd(g, Z, self.kstar, self.w, self.s, self.beta, self.H, self.sj)
+        be.factor_spmm_fwd(g, Z, self.kstar, self.w, self.s, self.beta, self.H, self.sj,
+                           self.dH if self.prescale else None)
         mark("spmm_fwd")
         all_gather_rows(self.H, part, self.group)
         mark("ag_H")

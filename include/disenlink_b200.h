@@ -136,18 +136,26 @@ int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float
  * one_minus_beta is passed separately because Python evaluates (1 - beta) in double.
  * sj_out (may be NULL): per-entry copy sj[e] = s[col[e], kstar[e]] of the normaliser the kernel
  * gathers anyway; handing it to dl_factor_bwd(_edges) saves the backward one gather per entry.
+ * zs_scratch (may be NULL): N*K*d floats of scratch.  When given, Z / s is written there in one
+ * streaming pass and the kernel gathers pre-normalised slices: one DRAM transaction per entry
+ * instead of two (slice + s[col,k]).  Only for graphs that are not row-partitioned (row_base == 0,
+ * every column < N), and exclusive with sj_out (DL_EINVAL otherwise).
  * hub_ws: dl_hub_scratch_floats(g, K*d) floats. */
 int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
                        const float* w, const float* s, int K, int d, float beta,
-                       float one_minus_beta, float* H, float* sj_out, float* hub_ws, dl_stream_t stream);
+                       float one_minus_beta, float* H, float* sj_out, float* zs_scratch, float* hub_ws,
+                       dl_stream_t stream);
 
 /* (4) backward of (2)+(3) w.r.t. Z given G = dL/dH.  dZ is ACCUMULATED into (it may already
  * hold the decoder's direct gradient); r [N,K] is scratch/output.  Closed form in DESIGN.md.
  * [ref: autograd of model.py:56-75].  sj (may be NULL): the sj_out of dl_factor_spmm_fwd.
+ * sr_scratch (may be NULL): 2 * n_nodes * K floats of scratch, n_nodes = number of rows of s and r
+ * (all nodes, not only the local rows): pass 2 packs (s, r) there and gathers both with one access.
  * hub_ws: dl_hub_scratch_floats(g, K*d) floats. */
 int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const uint8_t* kstar,
-                  const float* w, const float* s, const float* sj, int K, int d, float beta,
-                  float one_minus_beta, float T, float* dZ, float* r, float* hub_ws, dl_stream_t stream);
+                  const float* w, const float* s, const float* sj, float* sr_scratch, int64_t n_nodes,
+                  int K, int d, float beta, float one_minus_beta, float T, float* dZ, float* r,
+                  float* hub_ws, dl_stream_t stream);
 /* The two passes of dl_factor_bwd on their own (a node-partitioned run all-gathers r between
  * them): pass 1 writes r and adds beta*G + T_ to dZ; pass 2 adds the attention-weight terms. */
 int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
@@ -156,8 +164,8 @@ int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
                          dl_stream_t stream);
 int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
                         const uint8_t* kstar, const float* w, const float* s, const float* r,
-                        const float* sj, int K, int d, float one_minus_beta, float T, float* dZ,
-                        float* hub_ws, dl_stream_t stream);
+                        const float* sj, float* sr_scratch, int64_t n_nodes, int K, int d,
+                        float one_minus_beta, float T, float* dZ, float* hub_ws, dl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (5) factor-weighted link-pair scoring over explicit (u,v) batches.

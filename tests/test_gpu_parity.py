@@ -287,6 +287,11 @@ def test_saved_normaliser_sj(dl, K, d):
     dZ0, r0 = ops.factor_bwd(g, Z, G, kstar, w, s, 0.5, 1.0)
     dZ1, r1 = ops.factor_bwd(g, Z, G, kstar, w, s, 0.5, 1.0, sj=sj)
     assert torch.equal(dZ0, dZ1) and torch.equal(r0, r1)
+    # pre-scaled aggregation (slices divided by s beforehand): same H up to the rounding of Z/s
+    H2 = ops.factor_spmm_fwd(g, Z, kstar, w, s, 0.5, zs=torch.empty_like(Z))
+    assert relerr(H2.cpu().numpy(), H0.cpu().numpy()) < ORA_TOL
+    with pytest.raises(ValueError):
+        ops.factor_spmm_fwd(g, Z, kstar, w, s, 0.5, sj=sj, zs=torch.empty_like(Z))
 
 
 def test_large_graph_properties(dl):

@@ -58,7 +58,7 @@ class OracleBackend:
         w[:g.nnz] = torch.from_numpy(ww)
         s[g.part.lo:g.part.hi] = torch.from_numpy(ss[g.part.lo:g.part.hi])
 
-    def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H, sj=None):
+    def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H, sj=None, zs=None):
         out = self.o.factor_spmm_fwd(g.rowptr, g.col, Z.numpy(), kstar[:g.nnz].numpy(), w[:g.nnz].numpy(),
                                      s.numpy(), beta)
         H[g.part.lo:g.part.hi] = torch.from_numpy(out[g.part.lo:g.part.hi])

@@ -23,7 +23,7 @@ def main(path, nnz, pairs):
                 cur["duration_ms_under_ncu"] = float(m.group(2))
     for k in kernels.values():
         k["traffic"] = k.get("dram_bytes_read", 0.0) + k.get("dram_bytes_write", 0.0)
-    phase_of = [("bwd_edges", "k_bwd_edges", nnz), ("attn_fwd", "k_attn_stream", nnz),
+    phase_of = [("bwd_edges", "k_bwd_edges", nnz), ("attn_fwd", "k_attn_", nnz),
                 ("spmm_fwd", "k_gather_stream<DlMap<8, 16>, 0>", nnz),
                 ("bwd_gather", "k_gather_stream<DlMap<8, 16>, 1>", nnz),
                 ("pair_fwd", "k_pair_score_fwd", pairs), ("pair_bwd", "k_pair_bwd_stream", pairs)]
