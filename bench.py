@@ -359,7 +359,7 @@ def run_native(args):
     # chain + empty rows (3); aggregation = gather + chain + empty rows (3); pair scoring fwd (1);
     # decoder backward = stream + chain + empty nodes (3); backward pass 1 (3); backward pass 2 =
     # stream + chain (2); weighted BCE forward+backward (2)
-    launches_per_step = 17
+    launches_per_step = 17 + (1 if step.prescale else 0)     # + the Z/s streaming pass on one GPU
     kernels = {}
     for kname in KERNEL_PHASES:
         ms = phase_ms[kname]

@@ -308,20 +308,24 @@ inline int fixup_blocks(long long n) {
 
 }  // namespace
 
-// Zs[i,k,:] = Z[i,k,:] / s[i,k]: one streaming pass (8*N*D bytes at full bandwidth) that takes the
+// Zs[i,k,:] = Z[i,k,:] * (1 / s[i,k]): one streaming pass (8*N*D bytes at full bandwidth) that takes the
 // s[col,k] gather -- one of the two DRAM transactions per entry -- out of the aggregation kernel
-static __global__ void k_scale_rows(const float* __restrict__ Z, const float* __restrict__ s, long long n_rows,
-                                    int K, int d, float* __restrict__ Zs) {
-  const long long D4 = (long long)K * d / 4, total = n_rows * D4;
-  const int d4 = d / 4;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const long long row = t / D4;
-    const int k = (int)((t - row * D4) / d4);
-    const float sk = __ldg(s + row * K + k);
-    float4 v = __ldg(reinterpret_cast<const float4*>(Z) + t);
-    v.x = __fdiv_rn(v.x, sk); v.y = __fdiv_rn(v.y, sk); v.z = __fdiv_rn(v.z, sk); v.w = __fdiv_rn(v.w, sk);
-    reinterpret_cast<float4*>(Zs)[t] = v;
+static __global__ void __launch_bounds__(256)
+k_scale_rows(const float* __restrict__ Z, const float* __restrict__ s, long long n_rows, int K, int d,
+             float* __restrict__ Zs) {
+  // one warp per row, lanes over the row's float4 chunks; s[row,k] is inverted once per chunk
+  const int lane = threadIdx.x & 31;
+  const int D4 = K * d / 4, d4 = d / 4;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += nwarps) {
+    const float4* zr = reinterpret_cast<const float4*>(Z) + row * D4;
+    float4* out = reinterpret_cast<float4*>(Zs) + row * D4;
+    for (int c = lane; c < D4; c += 32) {
+      const float rs = __fdiv_rn(1.0f, __ldg(s + row * K + c / d4));
+      float4 v = __ldg(zr + c);
+      v.x = __fmul_rn(v.x, rs); v.y = __fmul_rn(v.y, rs); v.z = __fmul_rn(v.z, rs); v.w = __fmul_rn(v.w, rs);
+      out[c] = v;
+    }
   }
 }
 
@@ -407,7 +411,7 @@ int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* ks
   // pre-scaled path: needs every gathered row inside [0, N) (a graph that is not row-partitioned)
   if (zs_scratch && (sj_out || g.row_base != 0)) return DL_EINVAL;
   if (zs_scratch && g.nnz > 0 && d % 4 == 0 && g.erow && !getenv("DL_NO_STREAM") && !getenv("DL_NO_PRESCALE")) {
-    k_scale_rows<<<148 * 8, 256, 0, st>>>(Z, s, g.N, K, d, zs_scratch);
+    k_scale_rows<<<148 * 16, 256, 0, st>>>(Z, s, g.N, K, d, zs_scratch);
     DL_LAUNCH_CHECK();
     rc = dl_launch_gather_stream(0, g, Z, zs_scratch, kstar, w, nullptr, K, d, beta, one_minus_beta, H, nullptr,
                                  hub_ws, st);
