@@ -127,7 +127,6 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
   // gathers and the own-row bookkeeping (prow = per-lane rows of the previous chunk of this warp)
   auto finish_meta = [&](FMeta& m, int prow) {
     const int ks = m.info;
-#ifndef FL_EXP_NOSR
     if (m.row >= 0) {
       if (sr) {                 // (s, r) interleaved per (node, factor): one 8-byte gather for both
         const float2 v = __ldg(sr + (long long)m.col * K + ks);
@@ -138,7 +137,6 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
         m.rj = fl_ldg_small(r + (long long)m.col * K + ks);
       }
     }
-#endif
     const int up = __shfl_up_sync(DL_FULL, m.row, EPS);
     const int wrap = __shfl_sync(DL_FULL, prow, (lane + 32 - EPS) & 31);
     const int prevE = lane >= EPS ? up : wrap;
@@ -158,21 +156,13 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
 #pragma unroll
     for (int e = 0; e < EPS; ++e) {
       const long long cc = __shfl_sync(DL_FULL, m.col, q * EPS + e);
-#ifdef FL_EXP_NOROWS
-      if (false)
-#else
       if (((vq >> e) & 1u) && pact)
-#endif
         fl_cp16(st + C::NB_OFF + e * ROWS + pdst, Z + cc * D + lane * 4);
     }
     {   // routed slices G[j, kstar]: lane group e copies the slice of entry e
       const long long cc = __shfl_sync(DL_FULL, m.col, q * EPS + grp);
       const int kk = __shfl_sync(DL_FULL, m.info, q * EPS + grp) >> 3;
-#ifndef FL_EXP_NOSLICE
       if (((vq >> grp) & 1u) && kap < C4)
-#else
-      if (false)
-#endif
         fl_cp16_small(st + C::SL_OFF + grp * C::SLB + kap * 16, G + cc * D + kk * d + kap * 4);
     }
     if ((m.nmask >> (q * EPS)) & ((1u << EPS) - 1u)) {

@@ -110,12 +110,6 @@ int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const
                             cudaStream_t st);
 int dl_gather_chain_add(const DlGraphDev& g, int K, int d, float* scratch, float* OUT, cudaStream_t st);
 
-// Backward pass 2 as two lean streaming kernels (bwd_split.cu); scratch = carries + chain scratch
-// (3 * n_ranges * K*d floats) followed by nnz floats for the per-entry scalar.
-int dl_launch_bwd_edges_split(const DlGraphDev& g, const float* Z, const float* G,
-                              const unsigned char* kstar, const float* w, const float* s, const float* r,
-                              int K, int d, float omb, float T, float* dZ, float* scratch, cudaStream_t st);
-
 // Streaming backward pass 2, fused single kernel (bwd_stream.cu).  Returns -1000 when (K, d) has no streaming
 // instantiation.
 int dl_launch_bwd_edges_stream(const DlGraphDev& g, const float* Z, const float* G,

@@ -436,12 +436,6 @@ int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   const long long D = (long long)K * d;
   int rc = -1000;
-  // two-kernel variant (bwd_split.cu): same speed as the fused kernel today (20.6 ms at nnz = 1e8),
-  // needs nnz extra floats of scratch; opt in with DL_BWD_SPLIT=1
-  if (!getenv("DL_NO_STREAM") && getenv("DL_BWD_SPLIT"))
-    rc = dl_launch_bwd_edges_split(g, Z, G, kstar, w, s, r, K, d, one_minus_beta, T, dZ, hub_ws, st);
-  if (rc == DL_OK) return DL_OK;
-  if (rc != -1000) return rc;
   // factor-per-lane kernel (bwd_fl.cu) for the K <= 8, d <= 16 shape class; DL_NO_FL=1 disables it.
   // The interleaved (s, r) gather is opt-in (DL_USE_SR=1): -3.5 % at C5, +3 % at 1/10 of it, both
   // inside the clock wander of a power-capped run

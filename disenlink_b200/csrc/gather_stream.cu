@@ -301,31 +301,6 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
     for (int p = 0; p < NP; ++p) acc[p] = dl_zero4();
   };
 
-  // L2 prefetch of the row vectors the epilogue of a row needs, one chunk before the row starts
-  auto prefetch_starts = [&](const Meta& m, int last_row_before) {
-#ifdef GS_EXP_PREFETCH
-    if (MODE == 2) return;
-    const int prev = __shfl_up_sync(DL_FULL, m.row, 1);
-    const bool start = m.row >= 0 && m.row != (lane == 0 ? last_row_before : prev);
-    if (start) {
-      const long long node = g.row_base + m.row;
-      const char* zp = reinterpret_cast<const char*>(Z + node * D);
-#pragma unroll
-      for (int l = 0; l < D * 4; l += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(zp + l));
-      if (MODE == 1) {
-        const char* gp = reinterpret_cast<const char*>(SRC + node * D);
-        const char* dp = reinterpret_cast<const char*>(OUT + node * D);
-#pragma unroll
-        for (int l = 0; l < D * 4; l += 128) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + l));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(dp + l));
-        }
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(s + node * K)));
-      }
-    }
-#endif
-  };
-
   long long c = cs.first(gw);
   Meta mA, mB, mC;
   load_meta(c, mA);
@@ -334,31 +309,15 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
   float sjA = 1.0f, sjB = 1.0f;
   // s == nullptr in MODE 0: SRC holds slices already divided by s (factor_fwd.cu k_scale_rows)
   if (MODE == 0 && s != nullptr && mA.ks != 255) sjA = gs_ldg_s(s + (long long)mA.col * K + mA.ks);
-#ifdef GS_EXP_SJLEAD
-  Meta mD;
-  long long cnn = cs.next(cn);
-  load_meta(cnn, mC);
-  float sjC = 1.0f;
-  if (MODE == 0 && s != nullptr && mB.ks != 255) sjB = gs_ldg_s(s + (long long)mB.col * K + mB.ks);
-#endif
   int buf = 0;
-  prefetch_starts(mA, -1);
   issue_slices(tile, mA);
   dl_cp_async_commit();
 
   while (c >= 0) {
-#ifdef GS_EXP_SJLEAD
-    // ids three chunks ahead, the s gather two chunks ahead, slices one chunk ahead
-    const long long cnnn = cs.next(cnn);
-    load_meta(cnnn, mD);
-    if (MODE == 0 && s != nullptr && mC.ks != 255) sjC = gs_ldg_s(s + (long long)mC.col * K + mC.ks);
-#else
     // pipeline: metadata two chunks ahead, s gather + slices one chunk ahead
     const long long cnn = cs.next(cn);
     load_meta(cnn, mC);
     if (MODE == 0 && s != nullptr && mB.ks != 255) sjB = gs_ldg_s(s + (long long)mB.col * K + mB.ks);
-#endif
-    prefetch_starts(mB, __shfl_sync(DL_FULL, mA.row, 31));
     issue_slices(tile + (buf ^ 1) * TILE_B, mB);
     dl_cp_async_commit();
     dl_cp_async_wait<1>();
@@ -443,15 +402,9 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
     }
     __syncwarp();
     buf ^= 1;
-#ifdef GS_EXP_SJLEAD
-    c = cn; cn = cnn; cnn = cnnn;
-    mA = mB; mB = mC; mC = mD;
-    sjA = sjB; sjB = sjC;
-#else
     c = cn; cn = cnn;
     mA = mB; mB = mC;
     sjA = sjB;
-#endif
   }
   if (cur_range >= 0) flush(true);
   dl_cp_async_wait<0>();
