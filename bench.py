@@ -298,6 +298,7 @@ def run_native(args):
         dist.all_reduce(t)
         nnz_global = int(t.item())
     Z = gen_Z(part.n_pad, K, d, 0, dev)   # every rank generates the same full Z; only own rows are "its"
+    pushed = step.register_input(Z)          # all-gathers as NVLink pushes when the ranks can map each other
     torch.cuda.synchronize(dev)
     t_setup = time.perf_counter() - t_setup
 
@@ -508,7 +509,9 @@ def run_native(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": wl["name"], "N": N, "E_directed": E, "nnz": nnz_global, "K": K, "d": d, "P": P,
-                   "beta": beta, "T": T, "parallelism": "1 GPU" if world == 1 else f"node-partitioned x{world}, NCCL all-gather",
+                   "beta": beta, "T": T, "parallelism": "1 GPU" if world == 1 else (
+                       f"node-partitioned x{world}, all-gathers pushed over NVLink peer memory (dl_push_slice)" if pushed
+                       else f"node-partitioned x{world}, NCCL all-gather"),
                    "l2": f"inputs exceed L2: Z alone is {N * D * 4 / 2**30:.1f} GiB vs 126 MB L2 (no flush needed)",
                    "value_definition": "nnz / (attention + aggregation + both backward passes"
                                        + (" + their all-gathers)" if world > 1 else ")")},

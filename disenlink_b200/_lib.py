@@ -69,6 +69,10 @@ SIGNATURES = {
     "dl_link_bce": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "dl_roc_auc_workspace_bytes": (_i64, [_i64]),
     "dl_roc_auc": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "dl_push_slice": (_int, [_vp, _vp, _int, _i64, _vp]),
+    "dl_enable_peer_access": (_int, [_int]),
+    "dl_ipc_open": (_int, [_vp, _vp]),
+    "dl_ipc_close": (_int, [_vp]),
     "dl_structured_negative_sampling": (_int, [_GP, _vp, _i64, _i64, _c.c_uint64, _int, _vp, _vp, _vp]),
 }
 

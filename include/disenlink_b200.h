@@ -247,6 +247,20 @@ int dl_structured_negative_sampling(const dl_graph* g_host, const int64_t* src, 
                                     uint64_t seed, int max_tries, int64_t* k_out, int* n_failed,
                                     dl_stream_t stream);
 
+/* ---- all-gather of a node-partitioned array as a push over NVLink peer memory ---------------
+ * The owner of a slice writes it into the same position of every peer's copy of the array:
+ * peer_dst[q] (host array of n_peers <= 15 device pointers, already offset to the slice, mapped into
+ * this process with CUDA IPC) receives the n_bytes at src.  All pointers 16-byte aligned.  The call
+ * only enqueues the kernel; the caller orders the ranks (a barrier after it, and none of the peers
+ * may still be reading the previous contents). */
+int dl_push_slice(const void* src, void* const* peer_dst, int n_peers, int64_t n_bytes, dl_stream_t stream);
+/* cudaDeviceEnablePeerAccess(peer_device) for the current device; DL_EINVAL if the pair has no P2P path. */
+int dl_enable_peer_access(int peer_device);
+/* Map / unmap a peer process's allocation for kernels of the CURRENT device: handle = the 64 bytes of the
+ * owner's cudaIpcMemHandle_t; base_out receives the base address of that allocation in this process. */
+int dl_ipc_open(const void* handle, void** base_out);
+int dl_ipc_close(void* base);
+
 #ifdef __cplusplus
 }
 #endif

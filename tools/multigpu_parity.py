@@ -38,6 +38,9 @@ def main():
     Zfull = bench.gen_Z(part.n_pad, K, d, 0, dev)
     Zin = torch.zeros_like(Zfull)
     Zin[part.lo:part.hi] = Zfull[part.lo:part.hi]        # a rank only has its own rows before the gather
+    pushed = part_step.register_input(Zin)
+    if rank == 0:
+        print('exchange:', 'NVLink push' if pushed else 'NCCL all-gather', flush=True)
     part_step.run(Zin)
     single = PartitionedLinkStep(src, dst, N, u, v, lab, wts, K, d, 0.5, 1.0, world=1, rank=0, device=dev)
     Zs = Zfull[:N].clone()
