@@ -254,3 +254,25 @@ def test_structured_negative_sampling_large_properties():
     assert not bool((edge_keys[pos] == i * n + k).any())
     cnt = torch.bincount(k, minlength=n).float()
     assert float(((cnt - e / n) ** 2 / (e / n)).sum()) < 1.2 * n
+
+
+@pytest.mark.parametrize("n_bytes", [0, 16, 4096 + 16, 1_000_003])
+def test_push_slice_kernel(n_bytes):
+    """dl_push_slice (the all-gather push of the partitioned step) with local buffers standing in for
+    the peers' copies: every destination receives exactly the slice, nothing around it is touched,
+    a byte tail that is not a multiple of 16 included."""
+    import ctypes
+    from disenlink_b200._lib import check, lib, stream_of
+    dev = torch.device(DEV)
+    g = torch.Generator(device=DEV).manual_seed(n_bytes)
+    src = torch.randint(0, 255, (n_bytes + 32,), dtype=torch.uint8, device=DEV, generator=g)
+    dsts = [torch.full((n_bytes + 64,), 7, dtype=torch.uint8, device=DEV) for _ in range(3)]
+    arr = (ctypes.c_void_p * 3)(*[d.data_ptr() + 16 for d in dsts])
+    check(lib().dl_push_slice(src.data_ptr() + 16, arr, 3, n_bytes, stream_of(dev)), "dl_push_slice")
+    torch.cuda.synchronize()
+    for d in dsts:
+        assert torch.equal(d[16:16 + n_bytes], src[16:16 + n_bytes])
+        assert bool((d[:16] == 7).all()) and bool((d[16 + n_bytes:] == 7).all())
+    # misaligned pointers are rejected, not silently mis-copied
+    bad = (ctypes.c_void_p * 1)(dsts[0].data_ptr() + 4)
+    assert lib().dl_push_slice(src.data_ptr() + 16, bad, 1, 64, stream_of(dev)) != 0
