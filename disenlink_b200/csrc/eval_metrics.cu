@@ -12,10 +12,9 @@
 // radix sort of (key, label); exclusive scan of the negative flags; then every positive finds the
 // two ends of its tie group (neighbour test, galloping + binary search only inside ties) and adds
 // negpre[first] + negpre[last + 1] to a 64-bit integer accumulator (integer atomics: the sum does
-// not depend on the order).  Library code: the sort and the scan are CUB; the rest is hand-written.
-#include <cub/cub.cuh>
-
+// not depend on the order).  The sort and the scan are the hand-written primitives of dl_prims.cuh.
 #include "dl_common.cuh"
+#include "dl_prims.cuh"
 
 namespace {
 
@@ -25,19 +24,15 @@ struct AucWs {
   size_t key_a, key_b, lab_a, lab_b, negpre, acc, cub, cub_bytes, total;
 };
 
-struct NegFlag {
-  __host__ __device__ unsigned operator()(unsigned char l) const { return l ? 0u : 1u; }
+struct NegFlag {                       // scan input: 1 for a negative
+  const unsigned char* lab;
+  __device__ __forceinline__ unsigned operator()(long long i) const { return lab[i] ? 0u : 1u; }
 };
-using NegIter = cub::TransformInputIterator<unsigned, NegFlag, const unsigned char*>;
 
 AucWs auc_ws_layout(long long P) {
   AucWs w;
   const size_t n = (size_t)(P > 0 ? P : 1);
-  size_t a = 0, b = 0;
-  unsigned* k = nullptr;
-  unsigned char* l = nullptr;
-  cub::DeviceRadixSort::SortPairs(nullptr, a, k, k, l, l, (long long)n, 0, 32);
-  cub::DeviceScan::ExclusiveSum(nullptr, b, NegIter(l, NegFlag()), k, (long long)n);
+  const size_t a = dlp::sort_ws_bytes((long long)n), b = dlp::scan_ws_bytes((long long)n, 4);
   size_t off = 0;
   w.key_a = off; off += ev_align256(n * 4);
   w.key_b = off; off += ev_align256(n * 4);
@@ -155,8 +150,12 @@ int dl_roc_auc(const float* score, const float* labels, int64_t P, double* out, 
     if (grid > 148 * 16) grid = 148 * 16;
     k_auc_keys<<<(int)grid, 256, 0, st>>>(score, labels, P, key_a, lab_a, acc);
     DL_LAUNCH_CHECK();
-    DL_CUDA_TRY(cub::DeviceRadixSort::SortPairs(base + w.cub, cub_bytes, key_a, key_b, lab_a, lab_b, P, 0, 32, st));
-    DL_CUDA_TRY(cub::DeviceScan::ExclusiveSum(base + w.cub, cub_bytes, NegIter(lab_b, NegFlag()), negpre, P, st));
+    (void)cub_bytes;
+    int rc = dlp::sort_pairs<unsigned, unsigned char>(key_a, key_b, lab_a, lab_b, P, 0, 32, base + w.cub, st);
+    if (rc) return rc;
+    rc = dlp::scan<false, unsigned>(NegFlag{lab_b}, dlp::StoreArr<unsigned>{negpre}, P, dlp::OpSum<unsigned>(), 0u,
+                                    base + w.cub, st);
+    if (rc) return rc;
     k_auc_ranksum<<<(int)grid, 256, 0, st>>>(key_b, lab_b, negpre, P, acc);
     DL_LAUNCH_CHECK();
   }

@@ -7,12 +7,10 @@
 // into the routing matrix.  Here the same set of non-zeros is produced as a CSR in
 // adj_sym.nonzero() order.
 //
-// Round-1 note: the device-wide key sort / unique / scan steps call CUB (header-only, compiled
-// into this library); the key construction, row-pointer, bucket, hub-item and incidence kernels
-// are hand-written.  See DESIGN.md "what is library code".
-#include <cub/cub.cuh>
-
+// The device-wide steps (radix sort of the keys, unique, scans) are the hand-written primitives of
+// dl_prims.cuh; no library code is involved.
 #include "dl_common.cuh"
+#include "dl_prims.cuh"
 
 namespace {
 
@@ -29,13 +27,8 @@ struct CsrWs {
   size_t cub_bytes;
 };
 
-size_t cub_bytes_for_csr(long long M, long long N) {
-  size_t a = 0, b = 0, c = 0;
-  unsigned long long* k = nullptr;
-  long long* x = nullptr;
-  cub::DeviceRadixSort::SortKeys(nullptr, a, k, k, M, 0, 64);
-  cub::DeviceSelect::Unique(nullptr, b, k, k, x, M);
-  cub::DeviceScan::InclusiveScan(nullptr, c, x, x, cub::Max(), N + 1);
+size_t cub_bytes_for_csr(long long M, long long N) {   // scratch of sort / unique / scan (largest of the three)
+  const size_t a = dlp::sort_ws_bytes(M), b = dlp::unique_ws_bytes(M), c = dlp::scan_ws_bytes(N + 1, 8);
   size_t m = a > b ? a : b;
   return m > c ? m : c;
 }
@@ -321,14 +314,16 @@ int dl_csr_build_rect(const int64_t* src, const int64_t* dst, int64_t E, int64_t
     k_make_keys<<<blocks_for(E), 256, 0, st>>>((const long long*)src, (const long long*)dst, E, n_rows,
                                                n_cols, symmetrize, bits, ka, status_out);
     DL_LAUNCH_CHECK();
-    DL_CUDA_TRY(cub::DeviceRadixSort::SortKeys(cub_ws, cub_bytes, ka, kb, M, 0, bits + row_bits, st));
-    DL_CUDA_TRY(cub::DeviceSelect::Unique(cub_ws, cub_bytes, kb, ka, (long long*)nnz_out, M, st));
+    int rc = dlp::sort_keys<unsigned long long>(ka, kb, M, 0, bits + row_bits, cub_ws, st);
+    if (rc) return rc;
+    rc = dlp::unique_sorted<unsigned long long>(kb, ka, (long long*)nnz_out, M, cub_ws, st);
+    if (rc) return rc;
     k_decode_keys<<<blocks_for(M), 256, 0, st>>>(ka, (const long long*)nnz_out, bits, col, marks);
     DL_LAUNCH_CHECK();
   }
-  DL_CUDA_TRY(cub::DeviceScan::InclusiveScan(cub_ws, cub_bytes, marks, (long long*)rowptr,
-                                             cub::Max(), N + 1, st));
-  return DL_OK;
+  (void)cub_bytes;
+  return dlp::scan<true, long long>(dlp::LoadArr<long long>{marks}, dlp::StoreArr<long long>{(long long*)rowptr}, N + 1,
+                                    dlp::OpMax<long long>(), 0LL, cub_ws, st);
 }
 
 int dl_csr_from_dense(const float* adj, int64_t N, int64_t* rowptr, int32_t* col, void* ws,
@@ -337,9 +332,7 @@ int dl_csr_from_dense(const float* adj, int64_t N, int64_t* rowptr, int32_t* col
   cudaStream_t st = (cudaStream_t)stream;
   if (!col) {
     // count pass: marks (in ws) -> inclusive sum scan -> rowptr
-    size_t cub_bytes = 0;
-    long long* x = nullptr;
-    cub::DeviceScan::InclusiveSum(nullptr, cub_bytes, x, x, N + 1);
+    const size_t cub_bytes = dlp::scan_ws_bytes(N + 1, 8);
     size_t need = align256((size_t)(N + 1) * 8) + align256(cub_bytes);
     if (!ws || ws_bytes < need) return DL_EWORKSPACE;
     long long* marks = (long long*)ws;
@@ -349,8 +342,8 @@ int dl_csr_from_dense(const float* adj, int64_t N, int64_t* rowptr, int32_t* col
       k_dense_count<<<blocks_for(N * 32), 256, 0, st>>>(adj, N, marks);
       DL_LAUNCH_CHECK();
     }
-    DL_CUDA_TRY(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, marks, (long long*)rowptr, N + 1, st));
-    return DL_OK;
+    return dlp::scan<true, long long>(dlp::LoadArr<long long>{marks}, dlp::StoreArr<long long>{(long long*)rowptr},
+                                      N + 1, dlp::OpSum<long long>(), 0LL, cub_ws, st);
   }
   if (N > 0) {
     k_dense_fill<<<blocks_for(N * 32), 256, 0, st>>>(adj, N, (const long long*)rowptr, col);
@@ -381,13 +374,7 @@ int dl_rev_index(const int64_t* rowptr, const int32_t* col, int64_t N, int64_t n
   return DL_OK;
 }
 
-static size_t bucket_cub_bytes(long long N) {
-  size_t a = 0;
-  unsigned char* k = nullptr;
-  int* v = nullptr;
-  cub::DeviceRadixSort::SortPairs(nullptr, a, k, k, v, v, N > 0 ? N : 1, 0, 6);
-  return a;
-}
+static size_t bucket_cub_bytes(long long N) { return dlp::sort_ws_bytes(N > 0 ? N : 1); }
 
 size_t dl_degree_buckets_workspace_bytes(int64_t N) {
   if (N < 0) return 0;
@@ -410,8 +397,9 @@ int dl_degree_buckets(const int64_t* rowptr, int64_t N, int32_t* perm, int64_t* 
   if (N > 0) {
     k_degree_keys<<<blocks_for(N), 256, 0, st>>>((const long long*)rowptr, N, key_in, rowid);
     DL_LAUNCH_CHECK();
-    DL_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, key_in, key_out, rowid, perm, N,
-                                                0, 6, st));
+    (void)cub_bytes;
+    int rc = dlp::sort_pairs<unsigned char, int>(key_in, key_out, rowid, perm, N, 0, 6, cub_ws, st);
+    if (rc) return rc;
   }
   k_bucket_offsets<<<blocks_for(N > 0 ? N : 1), 256, 0, st>>>(key_out, N, (long long*)bucket_off);
   DL_LAUNCH_CHECK();
@@ -436,11 +424,7 @@ int dl_hub_items(const int64_t* rowptr, const int32_t* perm, int64_t n_hub, int6
 }
 
 static size_t incidence_cub_bytes(long long M, long long N) {
-  size_t a = 0, c = 0;
-  unsigned* k = nullptr;
-  long long* x = nullptr;
-  cub::DeviceRadixSort::SortPairs(nullptr, a, k, k, k, k, M > 0 ? M : 1, 0, 32);
-  cub::DeviceScan::InclusiveScan(nullptr, c, x, x, cub::Max(), N + 1);
+  const size_t a = dlp::sort_ws_bytes(M > 0 ? M : 1), c = dlp::scan_ws_bytes(N + 1, 8);
   return a > c ? a : c;
 }
 
@@ -480,15 +464,15 @@ int dl_pair_incidence_range(const int32_t* u, const int32_t* v, int64_t P, int64
     k_incidence_keys<<<blocks_for(P), 256, 0, st>>>(u, v, P, row_lo, row_hi, key_in, val_in);
     DL_LAUNCH_CHECK();
     const int bits = dl_bits_for(N + 1 > 1 ? N + 1 : 2);
-    DL_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, key_in, key_out, val_in, val_out,
-                                                M, 0, bits, st));
+    int rc = dlp::sort_pairs<unsigned, unsigned>(key_in, key_out, val_in, val_out, M, 0, bits, cub_ws, st);
+    if (rc) return rc;
     k_incidence_decode<<<blocks_for(M), 256, 0, st>>>(key_out, val_out, u, v, M, (unsigned)N, inc_other,
                                                       inc_pair, marks);
     DL_LAUNCH_CHECK();
   }
-  DL_CUDA_TRY(cub::DeviceScan::InclusiveScan(cub_ws, cub_bytes, marks, (long long*)inc_ptr,
-                                             cub::Max(), N + 1, st));
-  return DL_OK;
+  (void)cub_bytes;
+  return dlp::scan<true, long long>(dlp::LoadArr<long long>{marks}, dlp::StoreArr<long long>{(long long*)inc_ptr}, N + 1,
+                                    dlp::OpMax<long long>(), 0LL, cub_ws, st);
 }
 
 }  // extern "C"
