@@ -21,6 +21,7 @@
 #include "../../include/disenlink_b200.h"
 
 #define DL_FULL 0xffffffffu
+#define DL_MAX_PEER_OUT 15
 #define DL_WARPS_PER_CTA 8
 #define DL_CTA (DL_WARPS_PER_CTA * 32)
 // the register-heavy, double-buffered row-gather kernels use small CTAs so the register file is
@@ -51,6 +52,13 @@ struct DlGraphDev {
   const int* __restrict__ item_hub;
   const int* __restrict__ erow;
   long long row_base;
+  // Node-partitioned runs: the peers' copies of the row array the kernel produces (H for the
+  // aggregation, dH for the decoder backward), full-size and indexed by global node id like the
+  // local one.  A kernel that finishes an owned row stores it into every peer as well, so the
+  // all-gather rides on the kernel (NVLink stores) instead of following it.  Set by the entry points
+  // from their peer arguments; 0 everywhere else.
+  float* peer_out[DL_MAX_PEER_OUT];
+  int n_peer_out;
 };
 
 static inline DlGraphDev dl_graph_dev(const dl_graph* g) {
@@ -63,7 +71,19 @@ static inline DlGraphDev dl_graph_dev(const dl_graph* g) {
   o.item_hub = g->item_hub;
   o.erow = g->erow;
   o.row_base = g->row_base;
+  o.n_peer_out = 0;
+  for (int q = 0; q < DL_MAX_PEER_OUT; ++q) o.peer_out[q] = nullptr;
   return o;
+}
+
+static inline int dl_set_peer_out(DlGraphDev& g, float* const* peers, int n_peers) {
+  if (n_peers < 0 || n_peers > DL_MAX_PEER_OUT || (n_peers > 0 && !peers)) return 0;
+  for (int q = 0; q < n_peers; ++q) {
+    if (!peers[q]) return 0;
+    g.peer_out[q] = peers[q];
+  }
+  g.n_peer_out = n_peers;
+  return 1;
 }
 
 static inline int dl_graph_ok(const dl_graph* g) {

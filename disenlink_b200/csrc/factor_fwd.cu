@@ -395,16 +395,17 @@ int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float
   return DL_OK;
 }
 
-int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
-                       const float* w, const float* s, int K, int d, float beta,
-                       float one_minus_beta, float* H, float* sj_out, float* zs_scratch, float* hub_ws,
-                       dl_stream_t stream) {
+static int spmm_fwd_impl(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
+                         const float* w, const float* s, int K, int d, float beta,
+                         float one_minus_beta, float* H, float* sj_out, float* zs_scratch, float* hub_ws,
+                         float* const* H_peers, int n_peers, dl_stream_t stream) {
   if (!dl_graph_ok(g_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
   if (g_host->N == 0) return DL_OK;
   if (!Z || !s || !H || (g_host->nnz > 0 && (!kstar || !w))) return DL_EINVAL;
   if (g_host->n_hub_items > 0 && !hub_ws) return DL_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  const DlGraphDev g = dl_graph_dev(g_host);
+  DlGraphDev g = dl_graph_dev(g_host);
+  if (!dl_set_peer_out(g, H_peers, n_peers)) return DL_EINVAL;
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
   // pre-scaled path: needs every gathered row inside [0, N) (a graph that is not row-partitioned)
@@ -442,7 +443,29 @@ int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* ks
     k_spmm_hub_fixup<<<fixup_blocks(g.n_hub * D), 256, 0, st>>>(g, D, Z, hub_ws, beta, one_minus_beta, H);
     DL_LAUNCH_CHECK();
   }
+  if (n_peers > 0) {                           // the row-per-warp paths do not push: one copy kernel does
+    void* dst[DL_MAX_PEER_OUT];
+    const long long off = g.row_base * (long long)K * d;
+    for (int q = 0; q < n_peers; ++q) dst[q] = H_peers[q] + off;
+    return dl_push_slice(H + off, dst, n_peers, (int64_t)g.N * K * d * 4, stream);
+  }
   return DL_OK;
+}
+
+int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
+                       const float* w, const float* s, int K, int d, float beta,
+                       float one_minus_beta, float* H, float* sj_out, float* zs_scratch, float* hub_ws,
+                       dl_stream_t stream) {
+  return spmm_fwd_impl(g_host, Z, kstar, w, s, K, d, beta, one_minus_beta, H, sj_out, zs_scratch, hub_ws, nullptr, 0,
+                       stream);
+}
+
+int dl_factor_spmm_fwd_push(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
+                            const float* w, const float* s, int K, int d, float beta,
+                            float one_minus_beta, float* H, float* sj_out, float* hub_ws,
+                            float* const* H_peers, int n_peers, dl_stream_t stream) {
+  return spmm_fwd_impl(g_host, Z, kstar, w, s, K, d, beta, one_minus_beta, H, sj_out, nullptr, hub_ws, H_peers,
+                       n_peers, stream);
 }
 
 }  // extern "C"

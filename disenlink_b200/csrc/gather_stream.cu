@@ -50,7 +50,7 @@ __host__ __device__ constexpr int carry_width(int mode, int K, int d) {
 }
 
 // ---- row epilogues on a flat accumulator held by one thread-strided warp (rare rows) ----------
-__device__ __forceinline__ void epilogue_flat(int mode, int lane, long long node, int K, int d,
+__device__ __forceinline__ void epilogue_flat(const DlGraphDev& g, int mode, int lane, long long node, int K, int d,
                                               const float* acc /* global or shared, flat */,
                                               const float* __restrict__ Z, const float* __restrict__ G,
                                               const float* __restrict__ s, float beta, float omb,
@@ -58,8 +58,10 @@ __device__ __forceinline__ void epilogue_flat(int mode, int lane, long long node
   const long long D = (long long)K * d;
   if (mode == 4) {                       // decoder backward: record = [dZ row | dH row], overwrite
     for (long long x = lane; x < D; x += 32) {
+      const float dh = acc ? acc[D + x] : 0.0f;
       OUT[node * D + x] = acc ? acc[x] : 0.0f;
-      r[node * D + x] = acc ? acc[D + x] : 0.0f;
+      r[node * D + x] = dh;
+      for (int q = 0; q < g.n_peer_out; ++q) g.peer_out[q][node * D + x] = dh;      // dH goes to the peers too
     }
   } else if (mode == 3) {                // plain accumulate (backward pass 2 partial sums)
     if (acc)
@@ -72,7 +74,9 @@ __device__ __forceinline__ void epilogue_flat(int mode, int lane, long long node
   } else if (mode == 0) {
     for (long long x = lane; x < D; x += 32) {
       const float v = acc ? acc[x] : 0.0f;
-      OUT[node * D + x] = __fadd_rn(__fmul_rn(beta, Z[node * D + x]), __fmul_rn(omb, v));
+      const float h = __fadd_rn(__fmul_rn(beta, Z[node * D + x]), __fmul_rn(omb, v));
+      OUT[node * D + x] = h;
+      for (int q = 0; q < g.n_peer_out; ++q) g.peer_out[q][node * D + x] = h;       // H goes to the peers too
     }
   } else {
     for (int k = 0; k < K; ++k) {
@@ -107,7 +111,7 @@ k_gather_empty_rows(DlGraphDev g, int mode, int K, int d, const float* __restric
     while (m) {
       const int l = __ffs(m) - 1;
       m &= m - 1;
-      epilogue_flat(mode, lane, g.row_base + r0 + l, K, d, nullptr, Z, G, s, beta, omb, OUT, r);
+      epilogue_flat(g, mode, lane, g.row_base + r0 + l, K, d, nullptr, Z, G, s, beta, omb, OUT, r);
     }
   }
 }
@@ -139,7 +143,7 @@ k_gather_chain(DlGraphDev g, int mode, int K, int d, const float* __restrict__ c
       acc[x] = v;
     }
     __syncwarp();
-    epilogue_flat(mode, lane, g.row_base + row, K, d, acc, Z, G, s, beta, omb, OUT, r);
+    epilogue_flat(g, mode, lane, g.row_base + row, K, d, acc, Z, G, s, beta, omb, OUT, r);
   }
 }
 
@@ -265,6 +269,9 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
             h.z = __fadd_rn(__fmul_rn(beta, zi.z), __fmul_rn(omb, acc[p].z));
             h.w = __fadd_rn(__fmul_rn(beta, zi.w), __fmul_rn(omb, acc[p].w));
             *reinterpret_cast<float4*>(OUT + node * D + o) = h;
+#pragma unroll 1
+            for (int q = 0; q < g.n_peer_out; ++q)            // the all-gather of H rides on the kernel
+              *reinterpret_cast<float4*>(g.peer_out[q] + node * D + o) = h;
           }
         } else {
 #pragma unroll

@@ -307,9 +307,9 @@ int dl_pair_score_fwd(const int32_t* u, const int32_t* v, int64_t P, const float
   return rc;
 }
 
-int dl_pair_score_bwd(const dl_graph* inc_host, const int32_t* inc_pair, const float* Z,
-                      const float* H, const float* dS, int K, int d, float T, float* dZ, float* dH,
-                      float* hub_ws, dl_stream_t stream) {
+static int pair_bwd_impl(const dl_graph* inc_host, const int32_t* inc_pair, const float* Z,
+                         const float* H, const float* dS, int K, int d, float T, float* dZ, float* dH,
+                         float* hub_ws, float* const* dH_peers, int n_peers, dl_stream_t stream) {
   if (!dl_graph_ok(inc_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
   if (inc_host->N == 0) return DL_OK;
   if (!Z || !H || !dZ || !dH) return DL_EINVAL;
@@ -317,7 +317,8 @@ int dl_pair_score_bwd(const dl_graph* inc_host, const int32_t* inc_pair, const f
   if (inc_host->n_hub_items > 0 && !hub_ws) return DL_EINVAL;
   if (!(T == T) || T == 0.0f) return DL_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  const DlGraphDev g = dl_graph_dev(inc_host);
+  DlGraphDev g = dl_graph_dev(inc_host);
+  if (!dl_set_peer_out(g, dH_peers, n_peers)) return DL_EINVAL;
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
   if (!getenv("DL_NO_STREAM"))
@@ -344,7 +345,25 @@ int dl_pair_score_bwd(const dl_graph* inc_host, const int32_t* inc_pair, const f
     k_pair_bwd_hub_fixup<<<(int)b, 256, 0, st>>>(g, D, hub_ws, dZ, dH);
     DL_LAUNCH_CHECK();
   }
+  if (n_peers > 0) {                           // the row-per-warp paths do not push: one copy kernel does
+    void* dst[DL_MAX_PEER_OUT];
+    const long long off = g.row_base * (long long)K * d;
+    for (int q = 0; q < n_peers; ++q) dst[q] = dH_peers[q] + off;
+    return dl_push_slice(dH + off, dst, n_peers, (int64_t)g.N * K * d * 4, stream);
+  }
   return DL_OK;
+}
+
+int dl_pair_score_bwd(const dl_graph* inc_host, const int32_t* inc_pair, const float* Z,
+                      const float* H, const float* dS, int K, int d, float T, float* dZ, float* dH,
+                      float* hub_ws, dl_stream_t stream) {
+  return pair_bwd_impl(inc_host, inc_pair, Z, H, dS, K, d, T, dZ, dH, hub_ws, nullptr, 0, stream);
+}
+
+int dl_pair_score_bwd_push(const dl_graph* inc_host, const int32_t* inc_pair, const float* Z,
+                           const float* H, const float* dS, int K, int d, float T, float* dZ, float* dH,
+                           float* hub_ws, float* const* dH_peers, int n_peers, dl_stream_t stream) {
+  return pair_bwd_impl(inc_host, inc_pair, Z, H, dS, K, d, T, dZ, dH, hub_ws, dH_peers, n_peers, stream);
 }
 
 }  // extern "C"

@@ -131,6 +131,11 @@ k_pair_bwd_stream(DlGraphDev g, const int* __restrict__ inc_pair, const float* _
         if (!act[p]) continue;
         *reinterpret_cast<float4*>(dz_dst + off[p]) = az[p];
         *reinterpret_cast<float4*>(dh_dst + off[p]) = ah[p];
+        if (!(to_head || to_tail)) {
+#pragma unroll 1
+          for (int q = 0; q < g.n_peer_out; ++q)              // the all-gather of dH rides on the kernel
+            *reinterpret_cast<float4*>(g.peer_out[q] + (g.row_base + cur_row) * D + off[p]) = ah[p];
+        }
       }
       first_run = false;
     }

@@ -147,6 +147,17 @@ class PeerExchange:
         self.peers[t.data_ptr()] = ((ctypes.c_void_p * len(bases)), bases)
         return True
 
+    def peer_array(self, full: torch.Tensor):
+        """-> ctypes array of the peers' base pointers of `full` (for the *_push kernels), or None."""
+        reg = self.peers.get(full.data_ptr()) if self.available else None
+        if reg is None:
+            return None
+        arr_t, bases = reg
+        return arr_t(*bases)
+
+    def barrier(self) -> None:
+        dist.all_reduce(self._flag, group=self.group)
+
     def gather(self, full: torch.Tensor, per: int) -> bool:
         """Push rows [rank*per, (rank+1)*per) of `full` to every peer, then barrier.  -> False if
         `full` was not registered (the caller falls back to NCCL)."""
@@ -232,17 +243,32 @@ class CudaBackend:
     def edge_attn_fwd(self, g, Z, T, kstar, w, s):
         self.ops.edge_attn_fwd(g, Z, T, out=(kstar, w, s))
 
-    def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H, sj=None, zs=None):
-        self.ops.factor_spmm_fwd(g, Z, kstar, w, s, beta, out=H, sj=sj, zs=zs)
+    def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H, sj=None, zs=None, peers=None):
+        if peers is None:
+            self.ops.factor_spmm_fwd(g, Z, kstar, w, s, beta, out=H, sj=sj, zs=zs)
+            return
+        from ._lib import check, lib, ptr, stream_of
+        K, d = int(Z.shape[1]), int(Z.shape[2])
+        dev = Z.device
+        with torch.cuda.device(dev):          # aggregation with the all-gather of H fused in
+            check(lib().dl_factor_spmm_fwd_push(g.ref, ptr(Z), ptr(kstar), ptr(w), ptr(s), K, d, float(beta),
+                                                self.ops.one_minus(beta), ptr(H), ptr(sj) if sj is not None else None,
+                                                ptr(g.hub_scratch(K * d)), peers, len(peers), stream_of(dev)),
+                  "dl_factor_spmm_fwd_push")
 
     def pair_score_fwd(self, Z, H, shard, T, prob_slice):
         self.ops.pair_score_fwd(Z, H, shard, T, out=(None, prob_slice))
 
-    def pair_score_bwd(self, inc, inc_pair, Z, H, dS, T, dZ, dH):
+    def pair_score_bwd(self, inc, inc_pair, Z, H, dS, T, dZ, dH, peers=None):
         from ._lib import check, lib, ptr, stream_of
         K, d = int(Z.shape[1]), int(Z.shape[2])
         dev = Z.device
         with torch.cuda.device(dev):
+            if peers is not None:             # decoder backward with the all-gather of dH fused in
+                check(lib().dl_pair_score_bwd_push(inc.ref, ptr(inc_pair), ptr(Z), ptr(H), ptr(dS), K, d, float(T),
+                                                   ptr(dZ), ptr(dH), ptr(inc.hub_scratch(2 * K * d)), peers,
+                                                   len(peers), stream_of(dev)), "dl_pair_score_bwd_push")
+                return
             check(lib().dl_pair_score_bwd(inc.ref, ptr(inc_pair), ptr(Z), ptr(H), ptr(dS), K, d, float(T),
                                           ptr(dZ), ptr(dH), ptr(inc.hub_scratch(2 * K * d)),
                                           stream_of(dev)), "dl_pair_score_bwd")
@@ -312,6 +338,12 @@ class PartitionedLinkStep:
         pushed too (otherwise Z goes through NCCL)."""
         return bool(self.px is not None and self.px.available and self.px.register(Z))
 
+    def _fused_peers(self, full):
+        """Peer pointers for a kernel that pushes its own output (None: exchange after the kernel)."""
+        if self.px is None or os.environ.get("DL_NO_FUSED_PUSH"):
+            return None
+        return self.px.peer_array(full)
+
     def _gather_rows(self, full):
         if not (self.px is not None and self.px.gather(full, self.part.per)):
             all_gather_rows(full, self.part, self.group)
@@ -329,10 +361,16 @@ class PartitionedLinkStep:
         mark("attn_fwd")
         self._gather_rows(self.s)
         mark("ag_s")
-        be.factor_spmm_fwd(g, Z, self.kstar, self.w, self.s, self.beta, self.H, self.sj,
-                           self.dH if self.prescale else None)
-        mark("spmm_fwd")
-        self._gather_rows(self.H)
+        hp = self._fused_peers(self.H)
+        if hp is not None:                    # the exchange of H rides on the kernel: only a barrier follows
+            be.factor_spmm_fwd(g, Z, self.kstar, self.w, self.s, self.beta, self.H, self.sj, None, hp)
+            mark("spmm_fwd")
+            self.px.barrier()
+        else:
+            be.factor_spmm_fwd(g, Z, self.kstar, self.w, self.s, self.beta, self.H, self.sj,
+                               self.dH if self.prescale else None)
+            mark("spmm_fwd")
+            self._gather_rows(self.H)
         mark("ag_H")
         lo = part.rank * self.p_per
         if self.p_hi > self.p_lo:
@@ -351,9 +389,15 @@ class PartitionedLinkStep:
 
     def backward(self, Z):
         part, be, g, mark = self.part, self.be, self.graph, self.mark
-        be.pair_score_bwd(self.inc, self.inc_pair, Z, self.H, self.dS, self.T, self.dZ, self.dH)
-        mark("pair_bwd")
-        self._gather_rows(self.dH)
+        dp = self._fused_peers(self.dH)
+        if dp is not None:
+            be.pair_score_bwd(self.inc, self.inc_pair, Z, self.H, self.dS, self.T, self.dZ, self.dH, dp)
+            mark("pair_bwd")
+            self.px.barrier()
+        else:
+            be.pair_score_bwd(self.inc, self.inc_pair, Z, self.H, self.dS, self.T, self.dZ, self.dH)
+            mark("pair_bwd")
+            self._gather_rows(self.dH)
         mark("ag_dH")
         be.factor_bwd_gather(g, Z, self.dH, self.kstar, self.w, self.s, self.beta, self.dZ, self.r)
         mark("bwd_gather")

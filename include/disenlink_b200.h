@@ -254,6 +254,19 @@ int dl_structured_negative_sampling(const dl_graph* g_host, const int64_t* src, 
  * only enqueues the kernel; the caller orders the ranks (a barrier after it, and none of the peers
  * may still be reading the previous contents). */
 int dl_push_slice(const void* src, void* const* peer_dst, int n_peers, int64_t n_bytes, dl_stream_t stream);
+/* The two kernels whose output is exchanged right after them, with the exchange fused in: every owned
+ * row they finish is stored into the local array AND into the same row of each peer's copy
+ * (H_peers / dH_peers: host arrays of n_peers <= 15 device pointers to the peers' full-size arrays,
+ * mapped with dl_ipc_open), so the all-gather overlaps the kernel instead of following it.  The
+ * caller still orders the ranks with a barrier afterwards.  Otherwise identical to
+ * dl_factor_spmm_fwd (without the zs_scratch path) and dl_pair_score_bwd. */
+int dl_factor_spmm_fwd_push(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
+                            const float* w, const float* s, int K, int d, float beta,
+                            float one_minus_beta, float* H, float* sj_out, float* hub_ws,
+                            float* const* H_peers, int n_peers, dl_stream_t stream);
+int dl_pair_score_bwd_push(const dl_graph* inc_host, const int32_t* inc_pair, const float* Z,
+                           const float* H, const float* dS, int K, int d, float T, float* dZ, float* dH,
+                           float* hub_ws, float* const* dH_peers, int n_peers, dl_stream_t stream);
 /* cudaDeviceEnablePeerAccess(peer_device) for the current device; DL_EINVAL if the pair has no P2P path. */
 int dl_enable_peer_access(int peer_device);
 /* Map / unmap a peer process's allocation for kernels of the CURRENT device: handle = the 64 bytes of the
