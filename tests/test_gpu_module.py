@@ -276,3 +276,47 @@ def test_push_slice_kernel(n_bytes):
     # misaligned pointers are rejected, not silently mis-copied
     bad = (ctypes.c_void_p * 1)(dsts[0].data_ptr() + 4)
     assert lib().dl_push_slice(src.data_ptr() + 16, bad, 1, 64, stream_of(dev)) != 0
+
+
+@pytest.mark.parametrize("K,d", [(8, 16), (5, 32), (3, 7)])
+def test_fused_exchange_kernels_write_every_peer(K, d):
+    """dl_factor_spmm_fwd_push / dl_pair_score_bwd_push with local buffers standing in for the peers'
+    copies: every peer receives, bit for bit, the rows the kernel wrote locally (streamed shapes push
+    from the row epilogues, chain and empty-row kernels; other shapes through dl_push_slice), and
+    nothing else in the peer arrays is touched."""
+    import ctypes
+    from disenlink_b200 import ops
+    from disenlink_b200._lib import check, lib, ptr, stream_of
+    from disenlink_b200.graph import Graph
+    rng = np.random.default_rng(K * 10 + d)
+    n = 5000
+    src = np.concatenate([rng.integers(0, n, 40000), np.full(3000, 7)])
+    dst = np.concatenate([rng.integers(0, n, 40000), rng.choice(n, 3000, replace=False)])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    g = Graph.from_edges(t(src), t(dst), n)
+    Z = t((rng.standard_normal((n, K, d)) * 0.3).astype(np.float32))
+    kstar, w, s = ops.edge_attn_fwd(g, Z, 1.0)
+    H_ref = ops.factor_spmm_fwd(g, Z, kstar, w, s, 0.5)
+    dev = torch.device(DEV)
+    peers = [torch.full_like(Z, 123.0) for _ in range(2)]
+    arr = (ctypes.c_void_p * 2)(*[p.data_ptr() for p in peers])
+    H = torch.empty_like(Z)
+    check(lib().dl_factor_spmm_fwd_push(g.ref, ptr(Z), ptr(kstar), ptr(w), ptr(s), K, d, 0.5, 0.5, ptr(H), None,
+                                        ptr(g.hub_scratch(K * d)), arr, 2, stream_of(dev)), "spmm push")
+    assert torch.equal(H, H_ref)
+    for p in peers:
+        assert torch.equal(p, H)
+    # decoder backward: dH goes to the peers, dZ stays local
+    P = 30000
+    batch = ops.PairBatch(t(rng.integers(0, n, P)), t(rng.integers(0, n, P)), n)
+    dS = t(rng.standard_normal(P).astype(np.float32))
+    dZ_ref, dH_ref = ops.pair_score_bwd(Z, H, batch, dS, 1.0)
+    inc, inc_pair = batch.incidence()
+    peers = [torch.full_like(Z, -5.0) for _ in range(3)]
+    arr = (ctypes.c_void_p * 3)(*[p.data_ptr() for p in peers])
+    dZ, dH = torch.empty_like(Z), torch.empty_like(Z)
+    check(lib().dl_pair_score_bwd_push(inc.ref, ptr(inc_pair), ptr(Z), ptr(H), ptr(dS), K, d, 1.0, ptr(dZ), ptr(dH),
+                                       ptr(inc.hub_scratch(2 * K * d)), arr, 3, stream_of(dev)), "pair bwd push")
+    assert torch.equal(dZ, dZ_ref) and torch.equal(dH, dH_ref)
+    for p in peers:
+        assert torch.equal(p, dH)
