@@ -367,6 +367,8 @@ def run_native(args):
     # decoder backward = stream + chain + empty nodes (3); backward pass 1 (3); backward pass 2 =
     # stream + chain (2); weighted BCE forward+backward (2)
     launches_per_step = 17 + (1 if step.prescale else 0)     # + the Z/s streaming pass on one GPU
+    if world > 1 and pushed:                                  # + dl_push_slice for Z, s, prob, r (and H, dH unless fused)
+        launches_per_step += 6 if os.environ.get("DL_NO_FUSED_PUSH") else 4
     kernels = {}
     for kname in KERNEL_PHASES:
         ms = phase_ms[kname]
