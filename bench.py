@@ -367,8 +367,8 @@ def run_native(args):
     # decoder backward = stream + chain + empty nodes (3); backward pass 1 (3); backward pass 2 =
     # stream + chain (2); weighted BCE forward+backward (2)
     launches_per_step = 17 + (1 if step.prescale else 0)     # + the Z/s streaming pass on one GPU
-    if world > 1 and pushed:                                  # + dl_push_slice for Z, s, prob, r (and H, dH unless fused)
-        launches_per_step += 6 if os.environ.get("DL_NO_FUSED_PUSH") else 4
+    if world > 1 and pushed:                                  # + dl_push_slice for Z, prob (and s, H, dH, r unless fused)
+        launches_per_step += 6 if os.environ.get("DL_NO_FUSED_PUSH") else 2
     kernels = {}
     for kname in KERNEL_PHASES:
         ms = phase_ms[kname]
@@ -518,7 +518,7 @@ def run_native(args):
         "data": "synthetic",
         "config": {"workload": wl["name"], "N": N, "E_directed": E, "nnz": nnz_global, "K": K, "d": d, "P": P,
                    "beta": beta, "T": T, "parallelism": "1 GPU" if world == 1 else (
-                       f"node-partitioned x{world}, exchanges over NVLink peer memory: H and dH stored into the peers by the kernels that produce them, Z/s/prob/r by dl_push_slice" if pushed
+                       f"node-partitioned x{world}, exchanges over NVLink peer memory: s, H, dH and r stored into the peers by the kernels that produce them, Z and the scores by dl_push_slice" if pushed
                        else f"node-partitioned x{world}, NCCL all-gather"),
                    "l2": f"inputs exceed L2: Z alone is {N * D * 4 / 2**30:.1f} GiB vs 126 MB L2 (no flush needed)",
                    "value_definition": "nnz / (attention + aggregation + both backward passes"

@@ -71,6 +71,8 @@ SIGNATURES = {
     "dl_roc_auc": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "dl_push_slice": (_int, [_vp, _vp, _int, _i64, _vp]),
     "dl_factor_spmm_fwd_push": (_int, [_GP, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp, _vp, _int, _vp]),
+    "dl_edge_attn_fwd_push": (_int, [_GP, _vp, _int, _int, _f, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "dl_factor_bwd_gather_push": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp, _vp, _int, _vp]),
     "dl_pair_score_bwd_push": (_int, [_GP, _vp, _vp, _vp, _vp, _int, _int, _f, _vp, _vp, _vp, _vp, _int, _vp]),
     "dl_enable_peer_access": (_int, [_int]),
     "dl_ipc_open": (_int, [_vp, _vp]),

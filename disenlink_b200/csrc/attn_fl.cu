@@ -168,7 +168,11 @@ k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __r
       const bool to_tail = !to_head && at_range_end && tail_open;
       if (grp == 0 && factive) {
         if (to_head || to_tail) carry[(cur_range * 2 + (to_tail ? 1 : 0)) * K + kap] = v;
-        else s[(g.row_base + cur_row) * K + kap] = (v == 0.0f) ? 1.0f : v;
+        else {
+          const float sv = (v == 0.0f) ? 1.0f : v;
+          s[(g.row_base + cur_row) * K + kap] = sv;
+          for (int q = 0; q < g.n_peer_out; ++q) g.peer_out[q][(g.row_base + cur_row) * K + kap] = sv;
+        }
       }
       first_run = false;
     }

@@ -385,16 +385,17 @@ int launch_bwd_edges(const DlGraphDev& g, long long n_items, const float* Z, con
 
 extern "C" {
 
-int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
-                         const uint8_t* kstar, const float* w, const float* s, int K, int d,
-                         float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
-                         dl_stream_t stream) {
+static int bwd_gather_impl(const dl_graph* g_host, const float* Z, const float* G,
+                           const uint8_t* kstar, const float* w, const float* s, int K, int d,
+                           float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
+                           float* const* r_peers, int n_peers, dl_stream_t stream) {
   if (!dl_graph_ok(g_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
   if (g_host->N == 0) return DL_OK;
   if (!Z || !G || !s || !dZ || !r || (g_host->nnz > 0 && (!kstar || !w))) return DL_EINVAL;
   if (g_host->n_hub_items > 0 && !hub_ws) return DL_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  const DlGraphDev g = dl_graph_dev(g_host);
+  DlGraphDev g = dl_graph_dev(g_host);
+  if (!dl_set_peer_out(g, r_peers, n_peers)) return DL_EINVAL;
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
   if (!getenv("DL_NO_STREAM"))
@@ -419,7 +420,29 @@ int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
     }
     rc = DL_OK;
   }
-  return rc;
+  if (rc) return rc;
+  if (n_peers > 0) {                           // the row-per-warp paths do not push: one copy kernel does
+    void* dst[DL_MAX_PEER_OUT];
+    const long long off = g.row_base * (long long)K;
+    for (int q = 0; q < n_peers; ++q) dst[q] = r_peers[q] + off;
+    return dl_push_slice(r + off, dst, n_peers, (int64_t)g.N * K * 4, stream);
+  }
+  return DL_OK;
+}
+
+int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
+                         const uint8_t* kstar, const float* w, const float* s, int K, int d,
+                         float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
+                         dl_stream_t stream) {
+  return bwd_gather_impl(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, hub_ws, nullptr, 0, stream);
+}
+
+int dl_factor_bwd_gather_push(const dl_graph* g_host, const float* Z, const float* G,
+                              const uint8_t* kstar, const float* w, const float* s, int K, int d,
+                              float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
+                              float* const* r_peers, int n_peers, dl_stream_t stream) {
+  return bwd_gather_impl(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, hub_ws, r_peers, n_peers,
+                         stream);
 }
 
 int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,

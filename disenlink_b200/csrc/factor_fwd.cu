@@ -349,15 +349,17 @@ size_t dl_hub_scratch_floats(const dl_graph* g_host, int64_t width) {
   return hub > stream ? hub : stream;
 }
 
-int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float T,
-                     uint8_t* kstar, float* w, float* s, float* hub_ws, dl_stream_t stream) {
+static int attn_fwd_impl(const dl_graph* g_host, const float* Z, int K, int d, float T,
+                         uint8_t* kstar, float* w, float* s, float* hub_ws, float* const* s_peers, int n_peers,
+                         dl_stream_t stream) {
   if (!dl_graph_ok(g_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
   if (g_host->N == 0) return DL_OK;
   if (!Z || !s || (g_host->nnz > 0 && (!kstar || !w))) return DL_EINVAL;
   if (g_host->n_hub_items > 0 && !hub_ws) return DL_EINVAL;
   if (!(T == T) || T == 0.0f) return DL_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  const DlGraphDev g = dl_graph_dev(g_host);
+  DlGraphDev g = dl_graph_dev(g_host);
+  if (!dl_set_peer_out(g, s_peers, n_peers)) return DL_EINVAL;
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
   bool stream_tried = false;
@@ -392,7 +394,24 @@ int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float
     k_attn_hub_fixup<<<fixup_blocks(g.n_hub * K), 256, 0, st>>>(g, K, hub_ws, s);
     DL_LAUNCH_CHECK();
   }
+  if (n_peers > 0 && !streamed) {              // the row-per-warp row sums do not push: one copy kernel does
+    void* dst[DL_MAX_PEER_OUT];
+    const long long off = g.row_base * (long long)K;
+    for (int q = 0; q < n_peers; ++q) dst[q] = s_peers[q] + off;
+    return dl_push_slice(s + off, dst, n_peers, (int64_t)g.N * K * 4, stream);
+  }
   return DL_OK;
+}
+
+int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float T,
+                     uint8_t* kstar, float* w, float* s, float* hub_ws, dl_stream_t stream) {
+  return attn_fwd_impl(g_host, Z, K, d, T, kstar, w, s, hub_ws, nullptr, 0, stream);
+}
+
+int dl_edge_attn_fwd_push(const dl_graph* g_host, const float* Z, int K, int d, float T,
+                          uint8_t* kstar, float* w, float* s, float* hub_ws, float* const* s_peers, int n_peers,
+                          dl_stream_t stream) {
+  return attn_fwd_impl(g_host, Z, K, d, T, kstar, w, s, hub_ws, s_peers, n_peers, stream);
 }
 
 static int spmm_fwd_impl(const dl_graph* g_host, const float* Z, const uint8_t* kstar,

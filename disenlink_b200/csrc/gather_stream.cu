@@ -69,7 +69,9 @@ __device__ __forceinline__ void epilogue_flat(const DlGraphDev& g, int mode, int
   } else if (mode == 2) {
     for (int k = lane; k < K; k += 32) {
       const float v = acc ? acc[k] : 0.0f;
-      OUT[node * K + k] = (v == 0.0f) ? 1.0f : v;
+      const float sv = (v == 0.0f) ? 1.0f : v;
+      OUT[node * K + k] = sv;
+      for (int q = 0; q < g.n_peer_out; ++q) g.peer_out[q][node * K + k] = sv;     // s goes to the peers too
     }
   } else if (mode == 0) {
     for (long long x = lane; x < D; x += 32) {
@@ -90,7 +92,11 @@ __device__ __forceinline__ void epilogue_flat(const DlGraphDev& g, int mode, int
         OUT[o] = __fadd_rn(OUT[o], __fmaf_rn(beta, G[o], tv));
       }
       for (int o = 16; o > 0; o >>= 1) part = __fadd_rn(part, __shfl_xor_sync(DL_FULL, part, o));
-      if (lane == 0) r[node * K + k] = __fdiv_rn(part, sk);
+      if (lane == 0) {
+        const float rv = __fdiv_rn(part, sk);
+        r[node * K + k] = rv;
+        for (int q = 0; q < g.n_peer_out; ++q) g.peer_out[q][node * K + k] = rv;   // r goes to the peers too
+      }
     }
   }
 }
@@ -256,7 +262,11 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
       } else {
         const long long node = g.row_base + cur_row;
         if (MODE == 2) {
-          if (lane < K) OUT[node * K + lane] = (acc2 == 0.0f) ? 1.0f : acc2;
+          if (lane < K) {
+            const float sv = (acc2 == 0.0f) ? 1.0f : acc2;
+            OUT[node * K + lane] = sv;
+            for (int q = 0; q < g.n_peer_out; ++q) g.peer_out[q][node * K + lane] = sv;
+          }
         } else if (MODE == 0) {
 #pragma unroll
           for (int p = 0; p < NP; ++p) {
@@ -286,7 +296,11 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
             tv.z = __fmul_rn(scale, acc[p].z); tv.w = __fmul_rn(scale, acc[p].w);
             const float4 zi = act ? zpre[p] : dl_zero4();
             const float dotzt = dl_group_sum<M>(dl_chunk_dot(zi, tv));
-            if (k < K && gg == 0) r[node * K + k] = __fdiv_rn(dotzt, sk);
+            if (k < K && gg == 0) {
+              const float rv = __fdiv_rn(dotzt, sk);
+              r[node * K + k] = rv;
+              for (int q = 0; q < g.n_peer_out; ++q) g.peer_out[q][node * K + k] = rv;
+            }
             if (act) {
               const float4 gi = gpre[p];
               float4* dp = reinterpret_cast<float4*>(OUT + node * D + o);

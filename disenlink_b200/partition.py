@@ -240,8 +240,17 @@ class CudaBackend:
         return shard, inc, inc_pair
 
     # -- kernels (all write only the owned rows of the full-size outputs) --
-    def edge_attn_fwd(self, g, Z, T, kstar, w, s):
-        self.ops.edge_attn_fwd(g, Z, T, out=(kstar, w, s))
+    def edge_attn_fwd(self, g, Z, T, kstar, w, s, peers=None):
+        if peers is None:
+            self.ops.edge_attn_fwd(g, Z, T, out=(kstar, w, s))
+            return
+        from ._lib import check, lib, ptr, stream_of
+        K, d = int(Z.shape[1]), int(Z.shape[2])
+        dev = Z.device
+        with torch.cuda.device(dev):          # attention + row sums with the all-gather of s fused in
+            check(lib().dl_edge_attn_fwd_push(g.ref, ptr(Z), K, d, float(T), ptr(kstar), ptr(w), ptr(s),
+                                              ptr(g.hub_scratch(K)), peers, len(peers), stream_of(dev)),
+                  "dl_edge_attn_fwd_push")
 
     def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H, sj=None, zs=None, peers=None):
         if peers is None:
@@ -278,8 +287,17 @@ class CudaBackend:
         loss, _ = self.ops.link_bce(prob, labels, weights, want_grad=True, dS=dS)
         return loss
 
-    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r):
-        self.ops.factor_bwd_gather(g, Z, G, kstar, w, s, beta, dZ, r)
+    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r, peers=None):
+        if peers is None:
+            self.ops.factor_bwd_gather(g, Z, G, kstar, w, s, beta, dZ, r)
+            return
+        from ._lib import check, lib, ptr, stream_of
+        K, d = int(Z.shape[1]), int(Z.shape[2])
+        dev = Z.device
+        with torch.cuda.device(dev):          # backward pass 1 with the all-gather of r fused in
+            check(lib().dl_factor_bwd_gather_push(g.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d, float(beta),
+                                                  self.ops.one_minus(beta), ptr(dZ), ptr(r), ptr(g.hub_scratch(K * d)),
+                                                  peers, len(peers), stream_of(dev)), "dl_factor_bwd_gather_push")
 
     def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ, sj=None):
         self.ops.factor_bwd_edges(g, Z, G, kstar, w, s, r, beta, T, dZ, sj=sj)
@@ -357,9 +375,15 @@ class PartitionedLinkStep:
         mark("begin")
         self._gather_rows(Z)
         mark("ag_Z")
-        be.edge_attn_fwd(g, Z, self.T, self.kstar, self.w, self.s)
-        mark("attn_fwd")
-        self._gather_rows(self.s)
+        sp = self._fused_peers(self.s)
+        if sp is not None:
+            be.edge_attn_fwd(g, Z, self.T, self.kstar, self.w, self.s, sp)
+            mark("attn_fwd")
+            self.px.barrier()
+        else:
+            be.edge_attn_fwd(g, Z, self.T, self.kstar, self.w, self.s)
+            mark("attn_fwd")
+            self._gather_rows(self.s)
         mark("ag_s")
         hp = self._fused_peers(self.H)
         if hp is not None:                    # the exchange of H rides on the kernel: only a barrier follows
@@ -399,9 +423,15 @@ class PartitionedLinkStep:
             mark("pair_bwd")
             self._gather_rows(self.dH)
         mark("ag_dH")
-        be.factor_bwd_gather(g, Z, self.dH, self.kstar, self.w, self.s, self.beta, self.dZ, self.r)
-        mark("bwd_gather")
-        self._gather_rows(self.r)
+        rp = self._fused_peers(self.r)
+        if rp is not None:
+            be.factor_bwd_gather(g, Z, self.dH, self.kstar, self.w, self.s, self.beta, self.dZ, self.r, rp)
+            mark("bwd_gather")
+            self.px.barrier()
+        else:
+            be.factor_bwd_gather(g, Z, self.dH, self.kstar, self.w, self.s, self.beta, self.dZ, self.r)
+            mark("bwd_gather")
+            self._gather_rows(self.r)
         mark("ag_r")
         be.factor_bwd_edges(g, Z, self.dH, self.kstar, self.w, self.s, self.r, self.beta, self.T, self.dZ, self.sj)
         mark("bwd_edges")

@@ -259,11 +259,19 @@ int dl_push_slice(const void* src, void* const* peer_dst, int n_peers, int64_t n
  * (H_peers / dH_peers: host arrays of n_peers <= 15 device pointers to the peers' full-size arrays,
  * mapped with dl_ipc_open), so the all-gather overlaps the kernel instead of following it.  The
  * caller still orders the ranks with a barrier afterwards.  Otherwise identical to
- * dl_factor_spmm_fwd (without the zs_scratch path) and dl_pair_score_bwd. */
+ * dl_factor_spmm_fwd (without the zs_scratch path) and dl_pair_score_bwd.  The same for the two small
+ * per-node arrays: dl_edge_attn_fwd_push stores s, dl_factor_bwd_gather_push stores r. */
 int dl_factor_spmm_fwd_push(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
                             const float* w, const float* s, int K, int d, float beta,
                             float one_minus_beta, float* H, float* sj_out, float* hub_ws,
                             float* const* H_peers, int n_peers, dl_stream_t stream);
+int dl_edge_attn_fwd_push(const dl_graph* g_host, const float* Z, int K, int d, float T,
+                          uint8_t* kstar, float* w, float* s, float* hub_ws, float* const* s_peers, int n_peers,
+                          dl_stream_t stream);
+int dl_factor_bwd_gather_push(const dl_graph* g_host, const float* Z, const float* G,
+                              const uint8_t* kstar, const float* w, const float* s, int K, int d,
+                              float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
+                              float* const* r_peers, int n_peers, dl_stream_t stream);
 int dl_pair_score_bwd_push(const dl_graph* inc_host, const int32_t* inc_pair, const float* Z,
                            const float* H, const float* dS, int K, int d, float T, float* dZ, float* dH,
                            float* hub_ws, float* const* dH_peers, int n_peers, dl_stream_t stream);

@@ -306,6 +306,27 @@ def test_fused_exchange_kernels_write_every_peer(K, d):
     assert torch.equal(H, H_ref)
     for p in peers:
         assert torch.equal(p, H)
+    # attention + row sums: s goes to the peers
+    s_peers = [torch.full_like(s, 9.0) for _ in range(2)]
+    arr = (ctypes.c_void_p * 2)(*[p.data_ptr() for p in s_peers])
+    k2, w2, s2 = torch.empty_like(kstar), torch.empty_like(w), torch.empty_like(s)
+    check(lib().dl_edge_attn_fwd_push(g.ref, ptr(Z), K, d, 1.0, ptr(k2), ptr(w2), ptr(s2), ptr(g.hub_scratch(K)),
+                                      arr, 2, stream_of(dev)), "attn push")
+    assert torch.equal(k2, kstar) and torch.equal(w2, w) and torch.equal(s2, s)
+    for p in s_peers:
+        assert torch.equal(p, s)
+    # backward pass 1: r goes to the peers, dZ stays local
+    G = t(rng.standard_normal((n, K, d)).astype(np.float32))
+    dZ_ref, r_ref = torch.zeros_like(Z), torch.empty_like(s)
+    ops.factor_bwd_gather(g, Z, G, kstar, w, s, 0.5, dZ_ref, r_ref)
+    r_peers = [torch.full_like(s, 9.0) for _ in range(2)]
+    arr = (ctypes.c_void_p * 2)(*[p.data_ptr() for p in r_peers])
+    dZ1, r1 = torch.zeros_like(Z), torch.empty_like(s)
+    check(lib().dl_factor_bwd_gather_push(g.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d, 0.5, 0.5, ptr(dZ1),
+                                          ptr(r1), ptr(g.hub_scratch(K * d)), arr, 2, stream_of(dev)), "bwd gather push")
+    assert torch.equal(dZ1, dZ_ref) and torch.equal(r1, r_ref)
+    for p in r_peers:
+        assert torch.equal(p, r_ref)
     # decoder backward: dH goes to the peers, dZ stays local
     P = 30000
     batch = ops.PairBatch(t(rng.integers(0, n, P)), t(rng.integers(0, n, P)), n)
