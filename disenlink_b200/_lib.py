@@ -20,6 +20,24 @@ DL_SEG = 512
 DL_N_BUCKETS = 33
 DL_HUB_BUCKET_END = 23
 
+# dl_graph.flags (kernel-path switches for A/B runs and for testing the non-default paths)
+DL_F_NO_STREAM, DL_F_NO_FL, DL_F_NO_FL_ATTN, DL_F_NO_PRESCALE = 1, 2, 4, 8
+DL_F_NO_SJ, DL_F_NO_SR, DL_F_NO_XDOT = 16, 32, 64
+_FLAG_NAMES = {"NO_STREAM": 1, "NO_FL": 2, "NO_FL_ATTN": 4, "NO_PRESCALE": 8, "NO_SJ": 16, "NO_SR": 32,
+               "NO_XDOT": 64}
+
+
+def default_flags() -> int:
+    """Flags a new Graph starts with: 0, or the comma-separated names in DL_FLAGS (e.g.
+    DL_FLAGS=NO_FL,NO_XDOT).  The environment is read here, on the host side; the library itself
+    has no global state."""
+    val = 0
+    for name in filter(None, (x.strip().upper() for x in os.environ.get("DL_FLAGS", "").split(","))):
+        if name not in _FLAG_NAMES:
+            raise ValueError(f"DL_FLAGS: unknown flag {name!r} (known: {sorted(_FLAG_NAMES)})")
+        val |= _FLAG_NAMES[name]
+    return val
+
 _c = ctypes
 _vp = _c.c_void_p
 _i64 = _c.c_int64
@@ -32,7 +50,7 @@ class DlGraph(_c.Structure):
     """Mirror of ``struct dl_graph``."""
     _fields_ = [("N", _i64), ("nnz", _i64), ("rowptr", _vp), ("col", _vp), ("perm", _vp),
                 ("n_hub", _i64), ("n_hub_items", _i64), ("hub_seg_ptr", _vp), ("item_hub", _vp),
-                ("erow", _vp), ("row_base", _i64)]
+                ("erow", _vp), ("row_base", _i64), ("flags", _c.c_uint32)]
 
 
 _GP = _c.POINTER(DlGraph)
@@ -53,9 +71,9 @@ SIGNATURES = {
     "dl_hub_scratch_floats": (_sz, [_GP, _i64]),
     "dl_edge_attn_fwd": (_int, [_GP, _vp, _int, _int, _f, _vp, _vp, _vp, _vp, _vp]),
     "dl_factor_spmm_fwd": (_int, [_GP, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp, _vp, _vp]),
-    "dl_factor_bwd": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _f, _f, _f, _vp, _vp, _vp, _vp]),
-    "dl_factor_bwd_gather": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp, _vp]),
-    "dl_factor_bwd_edges": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _f, _f, _vp, _vp, _vp]),
+    "dl_factor_bwd": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _int, _int, _f, _f, _f, _vp, _vp, _vp, _vp]),
+    "dl_factor_bwd_gather": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dl_factor_bwd_edges": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _int, _int, _f, _f, _vp, _vp, _vp]),
     "dl_pair_score_fwd": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _f, _vp, _vp, _vp]),
     "dl_pair_incidence_workspace_bytes": (_sz, [_i64, _i64]),
     "dl_pair_incidence": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -72,7 +90,7 @@ SIGNATURES = {
     "dl_push_slice": (_int, [_vp, _vp, _int, _i64, _vp]),
     "dl_factor_spmm_fwd_push": (_int, [_GP, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp, _vp, _int, _vp]),
     "dl_edge_attn_fwd_push": (_int, [_GP, _vp, _int, _int, _f, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
-    "dl_factor_bwd_gather_push": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp, _vp, _int, _vp]),
+    "dl_factor_bwd_gather_push": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "dl_pair_score_bwd_push": (_int, [_GP, _vp, _vp, _vp, _vp, _int, _int, _f, _vp, _vp, _vp, _vp, _int, _vp]),
     "dl_enable_peer_access": (_int, [_int]),
     "dl_ipc_open": (_int, [_vp, _vp]),

@@ -34,11 +34,15 @@ namespace {
 #ifndef FL_MAXW
 #define FL_MAXW 16
 #endif
-constexpr int FL_RING = FL_RING_N;   // stages per warp ring (FL_RING - 1 in flight)
+#ifndef FL_RING_X
+#define FL_RING_X 2
+#endif
 constexpr int FL_OWN = FL_OWN_N;     // staged own-row slots per stage; further rows of a step are read with plain loads
 
-template <int K_, int d_>
+// HAS_X: the per-entry dots <G[j,k*], Z[i,k*]> come from pass 1 (x array); no routed slice is staged
+template <int K_, int d_, bool HAS_X>
 struct FlCfg {
+  static constexpr int FL_RING = HAS_X ? FL_RING_X : FL_RING_N;   // stages per warp ring (FL_RING - 1 in flight)
   static constexpr int K = K_, d = d_, D = K_ * d_;
   static constexpr int LPE = 8;                       // lanes per entry (factors padded to 8)
   static constexpr int EPS = 32 / LPE;                // entries per step
@@ -53,7 +57,7 @@ struct FlCfg {
   static constexpr int OWN_B = 2 * ROWS + SRB;
   static constexpr int NB_OFF = 0;
   static constexpr int SL_OFF = EPS * ROWS;
-  static constexpr int OWN_OFF = SL_OFF + EPS * SLB;
+  static constexpr int OWN_OFF = SL_OFF + (HAS_X ? 0 : EPS * SLB);
   static constexpr int STAGE_B = OWN_OFF + FL_OWN * OWN_B;
   static constexpr int BUDGET = 226 * 1024;
   static constexpr int NW_RAW = BUDGET / (FL_RING * STAGE_B);
@@ -70,7 +74,7 @@ struct FMeta {
   int row, col;
   int info;            // kstar << 3 | need << 2 | rank: own-row slot of the entry inside its step, and
                        // whether the lane group that will process it currently holds another row
-  float sj, rj;
+  float sj, rj, xv;
   unsigned vmask, smask, nmask;   // warp-uniform: valid entries, row starts per step, need flags
 };
 
@@ -84,14 +88,16 @@ __device__ __forceinline__ float fl_dot(const float4 (&a)[C::C4], const float4 (
   return p[0];
 }
 
-template <int K_, int d_>
-__global__ void __launch_bounds__(FlCfg<K_, d_>::THREADS, 1)
+template <int K_, int d_, bool HAS_X>
+__global__ void __launch_bounds__(FlCfg<K_, d_, HAS_X>::THREADS, 1)
 k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restrict__ G,
                const unsigned char* __restrict__ kstar, const float* __restrict__ s,
                const float* __restrict__ r, const float* __restrict__ sj, const float2* __restrict__ sr,
-               float omb, float T, float* __restrict__ dZ, float* __restrict__ carry) {
-  using C = FlCfg<K_, d_>;
+               const float* __restrict__ xc, float omb, float T, float* __restrict__ dZ,
+               float* __restrict__ carry) {
+  using C = FlCfg<K_, d_, HAS_X>;
   constexpr int K = C::K, d = C::d, D = C::D, LPE = C::LPE, EPS = C::EPS, QPC = C::QPC, C4 = C::C4;
+  constexpr int FL_RING = C::FL_RING;
   constexpr int ROWS = C::ROWS, STAGE_B = C::STAGE_B, OWN_B = C::OWN_B;
   constexpr int PIECES = K * C4;                       // 16-byte pieces per row (<= 32)
   extern __shared__ __align__(128) unsigned char dl_smem_raw[];
@@ -114,12 +120,13 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
   cs.init(g.nnz, (long long)gridDim.x * C::NW);
 
   auto load_meta = [&](long long cc, FMeta& m) {
-    m.row = -1; m.col = 0; m.info = 0; m.sj = 1.0f; m.rj = 0.0f;
+    m.row = -1; m.col = 0; m.info = 0; m.sj = 1.0f; m.rj = 0.0f; m.xv = 0.0f;
     if (cc >= 0) {
       const long long e = cc * DL_CH + lane;
       if (e < g.nnz) {
         m.row = __ldg(g.erow + e); m.col = __ldg(g.col + e); m.info = __ldg(kstar + e);
         if (sj) m.sj = __ldg(sj + e);        // s[col, kstar] as the forward saw it: no gather needed
+        if (HAS_X) m.xv = __ldg(xc + e);     // <G[col,kstar], Z[row,kstar]> as pass 1 computed it
       }
     }
   };
@@ -159,7 +166,7 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
       if (((vq >> e) & 1u) && pact)
         fl_cp16(st + C::NB_OFF + e * ROWS + pdst, Z + cc * D + lane * 4);
     }
-    {   // routed slices G[j, kstar]: lane group e copies the slice of entry e
+    if (!HAS_X) {   // routed slices G[j, kstar]: lane group e copies the slice of entry e
       const long long cc = __shfl_sync(DL_FULL, m.col, q * EPS + grp);
       const int kk = __shfl_sync(DL_FULL, m.info, q * EPS + grp) >> 3;
       if (((vq >> grp) & 1u) && kap < C4)
@@ -230,7 +237,7 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
   };
 
   static_assert(EPS == 4, "info packs the own-row slot in 2 bits");
-  static_assert(FL_RING - 1 <= QPC / 2, "the next chunk's metadata is completed half a chunk ahead");
+  static_assert(C::FL_RING - 1 <= QPC / 2, "the next chunk's metadata is completed half a chunk ahead");
   long long c = cs.first(gw);
   FMeta mA, mB;
   load_meta(c, mA);
@@ -302,12 +309,11 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
             r_own = __ldg(r + node * K + kap);
           }
         }
-        float4 zj[C4], gje[C4];
+        float4 zj[C4];
 #pragma unroll
         for (int cc = 0; cc < C4; ++cc) {
           // (groups without a valid entry and idle factor lanes read stale bytes; they never reach dz)
           zj[cc] = fl_lds4((st + C::NB_OFF + grp * ROWS + myblk) ^ (cc << 4));
-          gje[cc] = fl_lds4(st + C::SL_OFF + grp * C::SLB + cc * 16);
         }
         float qv = fl_dot<C>(zi, zj);
         if (!unit_T) qv = __fdiv_rn(qv, T);
@@ -322,7 +328,15 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
         const float rsum = fl_rcp(sum);
         const float wv = __fmul_rn(eks, rsum);
         const float cij = __fmul_rn(omb, __shfl_sync(DL_FULL, fl_dot<C>(gi, zj), gbase + ks));
-        const float cji = __fmul_rn(omb, __shfl_sync(DL_FULL, fl_dot<C>(gje, zi), gbase + ks));
+        float cji;
+        if (HAS_X) {
+          cji = __fmul_rn(omb, __shfl_sync(DL_FULL, mA.xv, src));
+        } else {
+          float4 gje[C4];
+#pragma unroll
+          for (int cc = 0; cc < C4; ++cc) gje[cc] = fl_lds4(st + C::SL_OFF + grp * C::SLB + cc * 16);
+          cji = __fmul_rn(omb, __shfl_sync(DL_FULL, fl_dot<C>(gje, zi), gbase + ks));
+        }
         const float siv = __shfl_sync(DL_FULL, s_own, gbase + ks);
         const float riv = __shfl_sync(DL_FULL, r_own, gbase + ks);
         float dws = __fadd_rn(__fmul_rn(cij, fl_rcp(sjv)), __fmul_rn(cji, fl_rcp(siv)));
@@ -365,23 +379,24 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
   dl_cp_async_wait<0>();
 }
 
-template <int K_, int d_>
+template <int K_, int d_, bool HAS_X>
 struct FlLaunch {
   static int run(const DlGraphDev& g, const float* Z, const float* G, const unsigned char* kstar,
-                 const float* s, const float* r, const float* sj, const float2* sr, float omb, float T, float* dZ,
-                 float* carry, cudaStream_t st) {
-    using C = FlCfg<K_, d_>;
+                 const float* s, const float* r, const float* sj, const float2* sr, const float* x, float omb,
+                 float T, float* dZ, float* carry, cudaStream_t st) {
+    using C = FlCfg<K_, d_, HAS_X>;
     int dev = 0, sms = 0;
     DL_CUDA_TRY(cudaGetDevice(&dev));
     DL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    DL_CUDA_TRY(cudaFuncSetAttribute(k_bwd_edges_fl<K_, d_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DL_CUDA_TRY(cudaFuncSetAttribute(k_bwd_edges_fl<K_, d_, HAS_X>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)C::SMEM));
     const long long n_chunks = (g.nnz + DL_CH - 1) / DL_CH;
     const long long n_ranges = (n_chunks + DL_RANGE - 1) / DL_RANGE;
     long long grid = (n_ranges + C::NW - 1) / C::NW;
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
-    k_bwd_edges_fl<K_, d_><<<(int)grid, C::THREADS, C::SMEM, st>>>(g, Z, G, kstar, s, r, sj, sr, omb, T, dZ, carry);
+    k_bwd_edges_fl<K_, d_, HAS_X><<<(int)grid, C::THREADS, C::SMEM, st>>>(g, Z, G, kstar, s, r, sj, sr, x, omb, T, dZ,
+                                                                          carry);
     DL_LAUNCH_CHECK();
     return DL_OK;
   }
@@ -406,7 +421,8 @@ bool dl_bwd_edges_fl_has(int K, int d) {
 
 int dl_launch_bwd_edges_fl(const DlGraphDev& g, const float* Z, const float* G, const unsigned char* kstar,
                            const float* s, const float* r, const float* sj, float* sr_scratch, long long n_nodes,
-                           int K, int d, float omb, float T, float* dZ, float* scratch, cudaStream_t st) {
+                           const float* x, int K, int d, float omb, float T, float* dZ, float* scratch,
+                           cudaStream_t st) {
   if (!g.erow || g.nnz == 0 || !scratch || !dl_bwd_edges_fl_has(K, d)) return -1000;
   const float2* sr = nullptr;
   if (sr_scratch && n_nodes > 0) {
@@ -415,9 +431,14 @@ int dl_launch_bwd_edges_fl(const DlGraphDev& g, const float* Z, const float* G, 
     sr = reinterpret_cast<const float2*>(sr_scratch);
   }
   int rc = -1000;
-  if (K == 8 && d == 16) rc = FlLaunch<8, 16>::run(g, Z, G, kstar, s, r, sj, sr, omb, T, dZ, scratch, st);
-  else if (K == 8 && d == 8) rc = FlLaunch<8, 8>::run(g, Z, G, kstar, s, r, sj, sr, omb, T, dZ, scratch, st);
-  else if (K == 5 && d == 16) rc = FlLaunch<5, 16>::run(g, Z, G, kstar, s, r, sj, sr, omb, T, dZ, scratch, st);
+#define FL_CASE(KK, DD)                                                                                             \
+  if (K == KK && d == DD)                                                                                           \
+    rc = x ? FlLaunch<KK, DD, true>::run(g, Z, G, kstar, s, r, sj, sr, x, omb, T, dZ, scratch, st)                   \
+           : FlLaunch<KK, DD, false>::run(g, Z, G, kstar, s, r, sj, sr, nullptr, omb, T, dZ, scratch, st);
+  FL_CASE(8, 16)
+  FL_CASE(8, 8)
+  FL_CASE(5, 16)
+#undef FL_CASE
   if (rc != DL_OK) return rc;
   return dl_gather_chain_add(g, K, d, scratch, dZ, st);
 }

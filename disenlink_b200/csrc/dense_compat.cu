@@ -199,7 +199,7 @@ int dl_dense_att(const dl_graph* g_host, const uint8_t* kstar, const float* w, c
   return DL_OK;
 }
 
-int dl_abi_version(void) { return 1; }
+int dl_abi_version(void) { return 2; }
 
 const char* dl_error_string(int code) {
   switch (code) {

@@ -107,7 +107,9 @@ size_t dl_gather_stream_scratch_floats(long long nnz, int mode, int K, int d);
 int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const float* SRC,
                             const unsigned char* kstar, const float* w, const float* s, int K, int d,
                             float beta, float omb, float* OUT, float* r, float* scratch,
-                            cudaStream_t st);
+                            cudaStream_t st, float* xout = nullptr);
+// whether the streaming pass 1 of shape (K, d) leaves the per-entry dots in xout (needs d/4 a power of two)
+bool dl_gather_stream_has_x(int K, int d);
 int dl_gather_chain_add(const DlGraphDev& g, int K, int d, float* scratch, float* OUT, cudaStream_t st);
 
 // Streaming backward pass 2, fused single kernel (bwd_stream.cu).  Returns -1000 when (K, d) has no streaming
@@ -126,7 +128,8 @@ int dl_launch_pair_bwd_stream(const DlGraphDev& g, const int* inc_pair, const fl
 // Factor-per-lane backward pass 2 (bwd_fl.cu).  Returns -1000 when (K, d) has no instantiation.
 int dl_launch_bwd_edges_fl(const DlGraphDev& g, const float* Z, const float* G, const unsigned char* kstar,
                            const float* s, const float* r, const float* sj, float* sr_scratch, long long n_nodes,
-                           int K, int d, float omb, float T, float* dZ, float* scratch, cudaStream_t st);
+                           const float* x, int K, int d, float omb, float T, float* dZ, float* scratch,
+                           cudaStream_t st);
 
 // Factor-per-lane attention + row sums (attn_fl.cu).  Returns -1000 when (K, d) has no instantiation.
 int dl_gather_chain_rowsum(const DlGraphDev& g, int K, float* scratch, float* s_out, cudaStream_t st);

@@ -387,19 +387,25 @@ extern "C" {
 
 static int bwd_gather_impl(const dl_graph* g_host, const float* Z, const float* G,
                            const uint8_t* kstar, const float* w, const float* s, int K, int d,
-                           float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
-                           float* const* r_peers, int n_peers, dl_stream_t stream) {
+                           float beta, float one_minus_beta, float* dZ, float* r, float* x, int* x_valid_out,
+                           float* hub_ws, float* const* r_peers, int n_peers, dl_stream_t stream) {
+  if (x_valid_out) *x_valid_out = 0;
   if (!dl_graph_ok(g_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
   if (g_host->N == 0) return DL_OK;
   if (!Z || !G || !s || !dZ || !r || (g_host->nnz > 0 && (!kstar || !w))) return DL_EINVAL;
   if (g_host->n_hub_items > 0 && !hub_ws) return DL_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  const unsigned flags = g_host->flags;
   DlGraphDev g = dl_graph_dev(g_host);
   if (!dl_set_peer_out(g, r_peers, n_peers)) return DL_EINVAL;
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
-  if (!getenv("DL_NO_STREAM"))
-    rc = dl_launch_gather_stream(1, g, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, hub_ws, st);
+  if (!(flags & DL_F_NO_STREAM)) {
+    // the streaming pass 1 leaves x[e] = <G[j,k*], Z[i,k*]> for pass 2 when asked to
+    float* xo = (x && !(flags & DL_F_NO_XDOT) && dl_gather_stream_has_x(K, d)) ? x : nullptr;
+    rc = dl_launch_gather_stream(1, g, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, hub_ws, st, xo);
+    if (rc == DL_OK && xo && x_valid_out) *x_valid_out = 1;
+  }
   if (rc == DL_OK) return DL_OK;
   if (rc != -1000) return rc;
   rc = dl_launch_slice_gather(1, g, n_items, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r,
@@ -432,22 +438,23 @@ static int bwd_gather_impl(const dl_graph* g_host, const float* Z, const float* 
 
 int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
                          const uint8_t* kstar, const float* w, const float* s, int K, int d,
-                         float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
-                         dl_stream_t stream) {
-  return bwd_gather_impl(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, hub_ws, nullptr, 0, stream);
+                         float beta, float one_minus_beta, float* dZ, float* r, float* x, int* x_valid_out,
+                         float* hub_ws, dl_stream_t stream) {
+  return bwd_gather_impl(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, x, x_valid_out, hub_ws,
+                         nullptr, 0, stream);
 }
 
 int dl_factor_bwd_gather_push(const dl_graph* g_host, const float* Z, const float* G,
                               const uint8_t* kstar, const float* w, const float* s, int K, int d,
-                              float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
-                              float* const* r_peers, int n_peers, dl_stream_t stream) {
-  return bwd_gather_impl(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, hub_ws, r_peers, n_peers,
-                         stream);
+                              float beta, float one_minus_beta, float* dZ, float* r, float* x, int* x_valid_out,
+                              float* hub_ws, float* const* r_peers, int n_peers, dl_stream_t stream) {
+  return bwd_gather_impl(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, x, x_valid_out, hub_ws,
+                         r_peers, n_peers, stream);
 }
 
 int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
                         const uint8_t* kstar, const float* w, const float* s, const float* r,
-                        const float* sj, float* sr_scratch, int64_t n_nodes, int K, int d,
+                        const float* sj, float* sr_scratch, int64_t n_nodes, const float* x, int K, int d,
                         float one_minus_beta, float T, float* dZ, float* hub_ws, dl_stream_t stream) {
   if (!dl_graph_ok(g_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
   if (g_host->N == 0) return DL_OK;
@@ -455,20 +462,21 @@ int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
   if (g_host->n_hub_items > 0 && !hub_ws) return DL_EINVAL;
   if (!(T == T) || T == 0.0f) return DL_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  const unsigned flags = g_host->flags;
   const DlGraphDev g = dl_graph_dev(g_host);
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   const long long D = (long long)K * d;
   int rc = -1000;
-  // factor-per-lane kernel (bwd_fl.cu) for the K <= 8, d <= 16 shape class; DL_NO_FL=1 disables it.
-  // The interleaved (s, r) gather is opt-in (DL_USE_SR=1): -3.5 % at C5, +3 % at 1/10 of it, both
-  // inside the clock wander of a power-capped run
-  if (!getenv("DL_NO_STREAM") && !getenv("DL_NO_FL"))
-    rc = dl_launch_bwd_edges_fl(g, Z, G, kstar, s, r, getenv("DL_NO_SJ") ? nullptr : sj,
-                                getenv("DL_USE_SR") ? sr_scratch : nullptr, n_nodes, K, d, one_minus_beta, T, dZ, hub_ws,
-                                st);
+  // factor-per-lane kernel (bwd_fl.cu) for the K <= 8, d <= 16 shape class.  It reads the per-entry
+  // dot x pass 1 left behind (no second gather of the routed G slice) and gathers (s, r) of the
+  // neighbour packed in one 8-byte access; flags switch either off for A/B runs.
+  if (!(flags & (DL_F_NO_STREAM | DL_F_NO_FL)))
+    rc = dl_launch_bwd_edges_fl(g, Z, G, kstar, s, r, (flags & DL_F_NO_SJ) ? nullptr : sj,
+                                (flags & DL_F_NO_SR) ? nullptr : sr_scratch, n_nodes,
+                                (flags & DL_F_NO_XDOT) ? nullptr : x, K, d, one_minus_beta, T, dZ, hub_ws, st);
   if (rc == DL_OK) return DL_OK;
   if (rc != -1000) return rc;
-  if (!getenv("DL_NO_STREAM"))
+  if (!(flags & DL_F_NO_STREAM))
     rc = dl_launch_bwd_edges_stream(g, Z, G, kstar, s, r, K, d, one_minus_beta, T, dZ, hub_ws, st);
   if (rc == DL_OK) return DL_OK;
   if (rc != -1000) return rc;
@@ -493,15 +501,16 @@ int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
 }
 
 int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const uint8_t* kstar,
-                  const float* w, const float* s, const float* sj, float* sr_scratch, int64_t n_nodes, int K,
-                  int d, float beta, float one_minus_beta, float T, float* dZ, float* r, float* hub_ws,
-                  dl_stream_t stream) {
+                  const float* w, const float* s, const float* sj, float* sr_scratch, int64_t n_nodes,
+                  float* x_scratch, int K, int d, float beta, float one_minus_beta, float T, float* dZ,
+                  float* r, float* hub_ws, dl_stream_t stream) {
   if (!(T == T) || T == 0.0f) return DL_EINVAL;
-  int rc = dl_factor_bwd_gather(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, hub_ws,
-                                stream);
+  int x_valid = 0;
+  int rc = dl_factor_bwd_gather(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, x_scratch,
+                                &x_valid, hub_ws, stream);
   if (rc) return rc;
-  return dl_factor_bwd_edges(g_host, Z, G, kstar, w, s, r, sj, sr_scratch, n_nodes, K, d, one_minus_beta, T, dZ,
-                             hub_ws, stream);
+  return dl_factor_bwd_edges(g_host, Z, G, kstar, w, s, r, sj, sr_scratch, n_nodes,
+                             x_valid ? x_scratch : nullptr, K, d, one_minus_beta, T, dZ, hub_ws, stream);
 }
 
 }  // extern "C"

@@ -358,18 +358,20 @@ static int attn_fwd_impl(const dl_graph* g_host, const float* Z, int K, int d, f
   if (g_host->n_hub_items > 0 && !hub_ws) return DL_EINVAL;
   if (!(T == T) || T == 0.0f) return DL_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  const unsigned flags = g_host->flags;
+  const bool no_stream = (flags & DL_F_NO_STREAM) != 0;
   DlGraphDev g = dl_graph_dev(g_host);
   if (!dl_set_peer_out(g, s_peers, n_peers)) return DL_EINVAL;
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
   bool stream_tried = false;
-  // factor-per-lane kernel (attn_fl.cu): routing and row sums in one launch; DL_NO_FL=1 disables it
-  if (g.erow && g.nnz > 0 && !getenv("DL_NO_STREAM") && !getenv("DL_NO_FL") && !getenv("DL_NO_FL_ATTN")) {
+  // factor-per-lane kernel (attn_fl.cu): routing and row sums in one launch
+  if (g.erow && g.nnz > 0 && !(flags & (DL_F_NO_STREAM | DL_F_NO_FL | DL_F_NO_FL_ATTN))) {
     rc = dl_launch_attn_fl(g, Z, K, d, T, kstar, w, s, hub_ws, st);
     if (rc == DL_OK) return DL_OK;
     if (rc != -1000) return rc;
   }
-  if (g.erow && g.nnz > 0 && !getenv("DL_NO_STREAM")) {
+  if (g.erow && g.nnz > 0 && !no_stream) {
     rc = dl_launch_attn_stream(g, g.erow, Z, K, d, T, kstar, w, s, hub_ws, st);
     stream_tried = (rc != -1000);
   }
@@ -388,7 +390,7 @@ static int attn_fwd_impl(const dl_graph* g_host, const float* Z, int K, int d, f
   }
   bool streamed = false;
   if (rc == -1001) { rc = DL_OK; }           // streamed routing, row sums by the row-per-warp kernel
-  else if (rc == DL_OK && g.erow && g.nnz > 0 && !getenv("DL_NO_STREAM") && stream_tried) streamed = true;
+  else if (rc == DL_OK && g.erow && g.nnz > 0 && !no_stream && stream_tried) streamed = true;
   if (rc) return rc;
   if (g.n_hub > 0 && !streamed) {
     k_attn_hub_fixup<<<fixup_blocks(g.n_hub * K), 256, 0, st>>>(g, K, hub_ws, s);
@@ -423,13 +425,14 @@ static int spmm_fwd_impl(const dl_graph* g_host, const float* Z, const uint8_t* 
   if (!Z || !s || !H || (g_host->nnz > 0 && (!kstar || !w))) return DL_EINVAL;
   if (g_host->n_hub_items > 0 && !hub_ws) return DL_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  const unsigned flags = g_host->flags;
   DlGraphDev g = dl_graph_dev(g_host);
   if (!dl_set_peer_out(g, H_peers, n_peers)) return DL_EINVAL;
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
   // pre-scaled path: needs every gathered row inside [0, N) (a graph that is not row-partitioned)
   if (zs_scratch && (sj_out || g.row_base != 0)) return DL_EINVAL;
-  if (zs_scratch && g.nnz > 0 && d % 4 == 0 && g.erow && !getenv("DL_NO_STREAM") && !getenv("DL_NO_PRESCALE")) {
+  if (zs_scratch && g.nnz > 0 && d % 4 == 0 && g.erow && !(flags & (DL_F_NO_STREAM | DL_F_NO_PRESCALE))) {
     k_scale_rows<<<148 * 16, 256, 0, st>>>(Z, s, g.N, K, d, zs_scratch);
     DL_LAUNCH_CHECK();
     rc = dl_launch_gather_stream(0, g, Z, zs_scratch, kstar, w, nullptr, K, d, beta, one_minus_beta, H, nullptr,
@@ -437,7 +440,7 @@ static int spmm_fwd_impl(const dl_graph* g_host, const float* Z, const uint8_t* 
     if (rc == DL_OK) return DL_OK;
     if (rc != -1000) return rc;                // -1000: no streaming instantiation, the scratch goes unused
   }
-  if (!getenv("DL_NO_STREAM"))
+  if (!(flags & DL_F_NO_STREAM))
     rc = dl_launch_gather_stream(0, g, Z, Z, kstar, w, s, K, d, beta, one_minus_beta, H, sj_out, hub_ws, st);
   if (rc == DL_OK) return DL_OK;             // carries, chained rows and empty rows all handled
   if (rc != -1000) return rc;

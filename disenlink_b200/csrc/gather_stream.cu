@@ -159,7 +159,9 @@ struct GatherStreamCfg {
   static constexpr int SLB = M::d * 4;                                  // bytes of one routed slice
   static constexpr int TILE_B = (MODE == 2) ? 0 : DL_CH * SLB;          // one chunk of slices
   static constexpr int CF_B = (MODE == 2) ? 0 : DL_CH * 4;              // the chunk's coefficients
-  static constexpr size_t SMEM = (size_t)GS_WARPS * (2 * TILE_B + CF_B);
+  static constexpr int X_B = (MODE == 1) ? DL_CH * 4 : 0;               // the chunk's <G[j,k*], Z[i,k*]> dots
+  static constexpr int WARP_B = 2 * TILE_B + CF_B + X_B;
+  static constexpr size_t SMEM = (size_t)GS_WARPS * WARP_B;
 };
 
 template <class M, int MODE>
@@ -167,19 +169,24 @@ __global__ void __launch_bounds__(GS_WARPS * 32)
 k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restrict__ SRC,
                 const unsigned char* __restrict__ kstar, const float* __restrict__ w,
                 const float* __restrict__ s, float beta, float omb, float* __restrict__ OUT,
-                float* __restrict__ r, float* __restrict__ carry) {
+                float* __restrict__ r, float* __restrict__ carry, float* __restrict__ xout) {
   using C = GatherStreamCfg<M, MODE>;
   constexpr int K = M::K, d = M::d, D = M::D, NP = M::NP, L = M::L, LP = M::LP, FPP = M::FPP;
   constexpr int NG = 32 / LP, SLB = C::SLB, TILE_B = C::TILE_B;
   constexpr int W = (MODE == 2) ? K : D;
   extern __shared__ __align__(128) unsigned char dl_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* tile = dl_smem_raw + (size_t)warp * (2 * TILE_B + C::CF_B);
+  unsigned char* tile = dl_smem_raw + (size_t)warp * C::WARP_B;
   float* cfbuf = reinterpret_cast<float*>(tile + 2 * TILE_B);
+  float* xbuf = cfbuf + DL_CH;                      // MODE 1 only
   const long long gw = (long long)blockIdx.x * GS_WARPS + warp;
   const int grp = lane / LP, gg = lane % LP, slot = M::slot(lane);
   const bool glane = gg < L;
   const long long RE = (long long)DL_CH * DL_RANGE;
+  // lanes of one factor group (they walk the same entries, so they may shuffle among themselves
+  // while the other groups are elsewhere in the divergent walk)
+  const unsigned gmask = (LP >= 32) ? 0xffffffffu : (((1u << LP) - 1u) << (grp * LP));
+  const bool want_x = (MODE == 1) && (L == LP) && xout != nullptr;
 
   DlChunkStream cs;
   cs.init(g.nnz, (long long)gridDim.x * GS_WARPS);
@@ -416,12 +423,21 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
             const float cf = cfbuf[i];
             const float4 v = dl_lds4(sl + i * SLB + gg * 16);
             dl_fma4(acc[p], cf, v);
+            if (MODE == 1 && want_x) {
+              // x[e] = <G[j,k*], Z[i,k*]> in the canonical order (chunk chains + balanced tree): the
+              // row's own Z chunk is in zpre (loaded when the run started), the routed slice is v
+              float pd = dl_chunk_dot(v, zpre[p]);
+#pragma unroll
+              for (int off = 1; off < LP; off <<= 1) pd = __fadd_rn(pd, __shfl_xor_sync(gmask, pd, off));
+              if (gg == 0) xbuf[i] = pd;
+            }
           }
         }
         idx = end;
       }
     }
     __syncwarp();
+    if (MODE == 1 && want_x && mA.row >= 0) xout[c * DL_CH + lane] = xbuf[lane];
     buf ^= 1;
     c = cn; cn = cnn;
     mA = mB; mB = mC;
@@ -434,7 +450,7 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
 template <class M, int MODE>
 int launch_gather_stream(const DlGraphDev& g, const float* Z, const float* SRC,
                          const unsigned char* kstar, const float* w, const float* s, float beta,
-                         float omb, float* OUT, float* r, float* carry, cudaStream_t st) {
+                         float omb, float* OUT, float* r, float* carry, float* xout, cudaStream_t st) {
   using C = GatherStreamCfg<M, MODE>;
   if (C::SMEM > 200 * 1024) return -1000;
   if (C::SMEM > 48 * 1024)
@@ -453,7 +469,7 @@ int launch_gather_stream(const DlGraphDev& g, const float* Z, const float* SRC,
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   k_gather_stream<M, MODE><<<(int)grid, GS_WARPS * 32, C::SMEM, st>>>(g, Z, SRC, kstar, w, s, beta, omb, OUT,
-                                                                     r, carry);
+                                                                     r, carry, xout);
   DL_LAUNCH_CHECK();
   return DL_OK;
 }
@@ -479,7 +495,7 @@ size_t dl_gather_stream_scratch_floats(long long nnz, int mode, int K, int d) {
 int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const float* SRC,
                             const unsigned char* kstar, const float* w, const float* s, int K, int d,
                             float beta, float omb, float* OUT, float* r, float* scratch,
-                            cudaStream_t st) {
+                            cudaStream_t st, float* xout) {
   if (!g.erow || g.nnz == 0 || !scratch) return -1000;
   const long long RE = (long long)DL_CH * DL_RANGE;
   const long long n_ranges = (g.nnz + RE - 1) / RE;
@@ -488,9 +504,9 @@ int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const
   float* chain = scratch + (size_t)n_ranges * 2 * W;
   int rc = -1000;
 #define BODY_MACRO(M)                                                                                       \
-  rc = (mode == 0)   ? launch_gather_stream<M, 0>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, st)     \
-       : (mode == 1) ? launch_gather_stream<M, 1>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, st)     \
-                     : launch_gather_stream<M, 2>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, st);
+  rc = (mode == 0)   ? launch_gather_stream<M, 0>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, nullptr, st)  \
+       : (mode == 1) ? launch_gather_stream<M, 1>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, xout, st)     \
+                     : launch_gather_stream<M, 2>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, nullptr, st);
   DL_DISPATCH_SHAPES()
 #undef BODY_MACRO
   if (rc != DL_OK) return rc;
@@ -502,6 +518,14 @@ int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const
                                                                      OUT, r_node);
   DL_LAUNCH_CHECK();
   return DL_OK;
+}
+
+bool dl_gather_stream_has_x(int K, int d) {
+  bool has = false;
+#define BODY_MACRO(M) has = (M::L == M::LP);
+  DL_DISPATCH_SHAPES()
+#undef BODY_MACRO
+  return has;
 }
 
 // chain fix-up alone, adding the stitched partial sums into OUT (used by bwd_stream.cu)

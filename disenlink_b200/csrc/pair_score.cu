@@ -321,7 +321,7 @@ static int pair_bwd_impl(const dl_graph* inc_host, const int32_t* inc_pair, cons
   if (!dl_set_peer_out(g, dH_peers, n_peers)) return DL_EINVAL;
   const long long n_items = g.n_hub_items + (g.N - g.n_hub);
   int rc = -1000;
-  if (!getenv("DL_NO_STREAM"))
+  if (!(inc_host->flags & DL_F_NO_STREAM))
     rc = dl_launch_pair_bwd_stream(g, inc_pair, Z, H, dS, K, d, T, dZ, dH, hub_ws, st);
   if (rc == DL_OK) return DL_OK;
   if (rc != -1000) return rc;

@@ -39,6 +39,7 @@ class Graph:
         self.col = col.contiguous()
         self.nnz = int(col.numel())
         self._rev = None
+        self._flags = _lib.default_flags()
         self._build_items()
 
     # ------------------------------------------------------------------ constructors
@@ -139,12 +140,22 @@ class Graph:
                   "dl_entry_rows")
         self.struct = DlGraph(self.N, self.nnz, ptr(self.rowptr), ptr(self.col), ptr(self.perm),
                               self.n_hub, self.n_hub_items, ptr(self.hub_seg_ptr),
-                              ptr(self.item_hub), ptr(self.erow), self.row_base)
+                              ptr(self.item_hub), ptr(self.erow), self.row_base, self._flags)
         self._hub_ws = None
 
     @property
     def ref(self):
         return ctypes.byref(self.struct)
+
+    @property
+    def flags(self) -> int:
+        """dl_graph.flags: kernel-path switches (_lib.DL_F_*), 0 = the fast paths."""
+        return self._flags
+
+    @flags.setter
+    def flags(self, value: int) -> None:
+        self._flags = int(value)
+        self.struct.flags = self._flags
 
     def hub_scratch(self, width: int):
         """fp32 scratch for hub-row partials of `width` floats per segment (None if no hubs)."""

@@ -79,15 +79,37 @@ def factor_spmm_fwd(graph: Graph, Z, kstar, w, s, beta: float, out=None, sj=None
     return H
 
 
-def factor_bwd_gather(graph: Graph, Z, G, kstar, w, s, beta: float, dZ, r):
-    """Pass 1 of the backward: r [N,K] and dZ += beta*G + T_ (see csrc/factor_bwd.cu)."""
+def _x_scratch(graph: Graph):
+    """[nnz] scratch in which pass 1 leaves <G[j,k*], Z[i,k*]> per entry for pass 2 -- cached on the
+    graph handle."""
+    buf = getattr(graph, "_x_scratch", None)
+    if buf is None or buf.numel() < max(graph.nnz, 1):
+        buf = torch.empty(max(graph.nnz, 1), dtype=torch.float32, device=graph.device)
+        graph._x_scratch = buf
+    return buf
+
+
+def factor_bwd_gather(graph: Graph, Z, G, kstar, w, s, beta: float, dZ, r, x=None, peers=None):
+    """Pass 1 of the backward: r [N,K] and dZ += beta*G + T_ (see csrc/factor_bwd.cu).
+    `x` = optional f32 [nnz] buffer for the per-entry dots pass 2 can reuse; -> True when it was
+    filled (hand it to factor_bwd_edges only then).  `peers` = ctypes array of the peers' copies of r
+    (node-partitioned runs: the all-gather of r rides on the kernel)."""
     K, d = _check_Z(Z, graph.n_global)
     dev = Z.device
+    x_valid = ctypes.c_int(0)
     with torch.cuda.device(dev):
-        check(lib().dl_factor_bwd_gather(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d,
-                                         float(beta), one_minus(beta), ptr(dZ), ptr(r),
-                                         ptr(graph.hub_scratch(K * d)), stream_of(dev)),
-              "dl_factor_bwd_gather")
+        if peers is None:
+            check(lib().dl_factor_bwd_gather(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d,
+                                             float(beta), one_minus(beta), ptr(dZ), ptr(r), _optr(x),
+                                             ctypes.byref(x_valid), ptr(graph.hub_scratch(K * d)),
+                                             stream_of(dev)), "dl_factor_bwd_gather")
+        else:
+            check(lib().dl_factor_bwd_gather_push(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d,
+                                                  float(beta), one_minus(beta), ptr(dZ), ptr(r), _optr(x),
+                                                  ctypes.byref(x_valid), ptr(graph.hub_scratch(K * d)),
+                                                  peers, len(peers), stream_of(dev)),
+                  "dl_factor_bwd_gather_push")
+    return bool(x_valid.value)
 
 
 def _sr_scratch(graph: Graph, s):
@@ -99,13 +121,14 @@ def _sr_scratch(graph: Graph, s):
     return buf
 
 
-def factor_bwd_edges(graph: Graph, Z, G, kstar, w, s, r, beta: float, T: float, dZ, sj=None):
-    """Pass 2 of the backward: dZ += attention-weight terms (needs r of every neighbour)."""
+def factor_bwd_edges(graph: Graph, Z, G, kstar, w, s, r, beta: float, T: float, dZ, sj=None, x=None):
+    """Pass 2 of the backward: dZ += attention-weight terms (needs r of every neighbour).
+    `x` = the per-entry dots factor_bwd_gather filled (only if it returned True)."""
     K, d = _check_Z(Z, graph.n_global)
     dev = Z.device
     with torch.cuda.device(dev):
         check(lib().dl_factor_bwd_edges(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), ptr(r), _optr(sj),
-                                        ptr(_sr_scratch(graph, s)), int(s.shape[0]), K, d,
+                                        ptr(_sr_scratch(graph, s)), int(s.shape[0]), _optr(x), K, d,
                                         one_minus(beta), float(T), ptr(dZ),
                                         ptr(graph.hub_scratch(K * d)), stream_of(dev)),
               "dl_factor_bwd_edges")
@@ -124,7 +147,7 @@ def factor_bwd(graph: Graph, Z, G, kstar, w, s, beta: float, T: float = 1.0, dZ=
         if r is None:
             r = torch.empty(graph.n_global, K, dtype=torch.float32, device=dev)
         check(lib().dl_factor_bwd(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), _optr(sj),
-                                  ptr(_sr_scratch(graph, s)), int(s.shape[0]), K, d,
+                                  ptr(_sr_scratch(graph, s)), int(s.shape[0]), ptr(_x_scratch(graph)), K, d,
                                   float(beta), one_minus(beta), float(T), ptr(dZ), ptr(r),
                                   ptr(graph.hub_scratch(K * d)), stream_of(dev)), "dl_factor_bwd")
     return dZ, r

@@ -287,20 +287,12 @@ class CudaBackend:
         loss, _ = self.ops.link_bce(prob, labels, weights, want_grad=True, dS=dS)
         return loss
 
-    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r, peers=None):
-        if peers is None:
-            self.ops.factor_bwd_gather(g, Z, G, kstar, w, s, beta, dZ, r)
-            return
-        from ._lib import check, lib, ptr, stream_of
-        K, d = int(Z.shape[1]), int(Z.shape[2])
-        dev = Z.device
-        with torch.cuda.device(dev):          # backward pass 1 with the all-gather of r fused in
-            check(lib().dl_factor_bwd_gather_push(g.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d, float(beta),
-                                                  self.ops.one_minus(beta), ptr(dZ), ptr(r), ptr(g.hub_scratch(K * d)),
-                                                  peers, len(peers), stream_of(dev)), "dl_factor_bwd_gather_push")
+    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r, peers=None, x=None):
+        """-> True when x was filled (backward pass 1; with peers the all-gather of r is fused in)."""
+        return self.ops.factor_bwd_gather(g, Z, G, kstar, w, s, beta, dZ, r, x=x, peers=peers)
 
-    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ, sj=None):
-        self.ops.factor_bwd_edges(g, Z, G, kstar, w, s, r, beta, T, dZ, sj=sj)
+    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ, sj=None, x=None):
+        self.ops.factor_bwd_edges(g, Z, G, kstar, w, s, r, beta, T, dZ, sj=sj, x=x)
 
 
 class PartitionedLinkStep:
@@ -334,8 +326,9 @@ class PartitionedLinkStep:
         self.w = torch.empty(max(nnz, 1), **f32)
         # one rank: the aggregation gathers slices pre-divided by s (scratch = the dH buffer, idle
         # during the forward); several ranks: s[col, kstar] per local entry goes forward -> pass 2
-        self.prescale = (part.world == 1) and not os.environ.get("DL_NO_PRESCALE")
+        self.prescale = (part.world == 1) and not (getattr(self.graph, "flags", 0) & 8)    # _lib.DL_F_NO_PRESCALE
         self.sj = None if self.prescale else torch.empty(max(nnz, 1), **f32)
+        self.x = torch.empty(max(nnz, 1), **f32)   # <G[j,k*], Z[i,k*]> per entry: pass 1 -> pass 2
         self.s = torch.ones(part.n_pad, K, **f32)
         self.r = torch.zeros(part.n_pad, K, **f32)
         self.H = torch.zeros(part.n_pad, K, d, **f32)
@@ -425,15 +418,18 @@ class PartitionedLinkStep:
         mark("ag_dH")
         rp = self._fused_peers(self.r)
         if rp is not None:
-            be.factor_bwd_gather(g, Z, self.dH, self.kstar, self.w, self.s, self.beta, self.dZ, self.r, rp)
+            xv = be.factor_bwd_gather(g, Z, self.dH, self.kstar, self.w, self.s, self.beta, self.dZ, self.r, rp,
+                                      x=self.x)
             mark("bwd_gather")
             self.px.barrier()
         else:
-            be.factor_bwd_gather(g, Z, self.dH, self.kstar, self.w, self.s, self.beta, self.dZ, self.r)
+            xv = be.factor_bwd_gather(g, Z, self.dH, self.kstar, self.w, self.s, self.beta, self.dZ, self.r,
+                                      x=self.x)
             mark("bwd_gather")
             self._gather_rows(self.r)
         mark("ag_r")
-        be.factor_bwd_edges(g, Z, self.dH, self.kstar, self.w, self.s, self.r, self.beta, self.T, self.dZ, self.sj)
+        be.factor_bwd_edges(g, Z, self.dH, self.kstar, self.w, self.s, self.r, self.beta, self.T, self.dZ, self.sj,
+                            x=self.x if xv else None)
         mark("bwd_edges")
         return self.dZ
 

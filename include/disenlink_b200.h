@@ -118,7 +118,20 @@ typedef struct dl_graph {
                                   dZ) are indexed by row_base + row, i.e. they are full-size
                                   [N_global, ...] arrays of which this call reads every gathered
                                   row and writes only the owned slice */
+  uint32_t flags;              /* DL_F_* kernel-path switches; 0 = the fast paths.  Results are
+                                  identical up to the stated tolerances whatever the flags (they
+                                  exist for A/B measurements and for testing the other paths) */
 } dl_graph;
+
+/* dl_graph.flags */
+#define DL_F_NO_STREAM 1u     /* row-per-warp / generic kernels instead of the streaming ones */
+#define DL_F_NO_FL 2u         /* lane-per-chunk streaming kernels instead of the factor-per-lane ones */
+#define DL_F_NO_FL_ATTN 4u    /* ... for the attention kernel only */
+#define DL_F_NO_PRESCALE 8u   /* aggregation gathers s[col,k] per entry even when zs_scratch is given */
+#define DL_F_NO_SJ 16u        /* backward pass 2 ignores the per-entry s[col,kstar] copy */
+#define DL_F_NO_SR 32u        /* backward pass 2 gathers s and r separately instead of packed (s, r) */
+#define DL_F_NO_XDOT 64u      /* backward pass 2 re-gathers the G[j,kstar] slice instead of reading the
+                                 per-entry dot pass 1 left in x */
 
 /* ------------------------------------------------------------------------------------------
  * (2) per-edge K-factor attention with hard routing.
@@ -151,21 +164,28 @@ int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* ks
  * [ref: autograd of model.py:56-75].  sj (may be NULL): the sj_out of dl_factor_spmm_fwd.
  * sr_scratch (may be NULL): 2 * n_nodes * K floats of scratch, n_nodes = number of rows of s and r
  * (all nodes, not only the local rows): pass 2 packs (s, r) there and gathers both with one access.
+ * x_scratch (may be NULL): nnz floats, see dl_factor_bwd_gather.
  * hub_ws: dl_hub_scratch_floats(g, K*d) floats. */
 int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const uint8_t* kstar,
                   const float* w, const float* s, const float* sj, float* sr_scratch, int64_t n_nodes,
-                  int K, int d, float beta, float one_minus_beta, float T, float* dZ, float* r,
-                  float* hub_ws, dl_stream_t stream);
+                  float* x_scratch, int K, int d, float beta, float one_minus_beta, float T, float* dZ,
+                  float* r, float* hub_ws, dl_stream_t stream);
 /* The two passes of dl_factor_bwd on their own (a node-partitioned run all-gathers r between
- * them): pass 1 writes r and adds beta*G + T_ to dZ; pass 2 adds the attention-weight terms. */
+ * them): pass 1 writes r and adds beta*G + T_ to dZ; pass 2 adds the attention-weight terms.
+ * x (may be NULL): nnz floats.  Pass 1 holds, per entry e = (i,j), the routed slice G[j,kstar] it
+ * gathers and the row's own Z[i]: it leaves x[e] = <G[j,kstar], Z[i,kstar]> there (canonical dot
+ * order) and pass 2 reads those 4 bytes instead of gathering the 64-byte slice a second time.
+ * x_valid_out (host int, may be NULL) is set to 1 when the pass-1 path taken filled x (the
+ * streaming path), else 0; dl_factor_bwd_edges must only be given an x that was filled. */
 int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
                          const uint8_t* kstar, const float* w, const float* s, int K, int d,
-                         float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
-                         dl_stream_t stream);
+                         float beta, float one_minus_beta, float* dZ, float* r, float* x,
+                         int* x_valid_out, float* hub_ws, dl_stream_t stream);
 int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
                         const uint8_t* kstar, const float* w, const float* s, const float* r,
-                        const float* sj, float* sr_scratch, int64_t n_nodes, int K, int d,
-                        float one_minus_beta, float T, float* dZ, float* hub_ws, dl_stream_t stream);
+                        const float* sj, float* sr_scratch, int64_t n_nodes, const float* x, int K,
+                        int d, float one_minus_beta, float T, float* dZ, float* hub_ws,
+                        dl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (5) factor-weighted link-pair scoring over explicit (u,v) batches.
@@ -270,8 +290,9 @@ int dl_edge_attn_fwd_push(const dl_graph* g_host, const float* Z, int K, int d, 
                           dl_stream_t stream);
 int dl_factor_bwd_gather_push(const dl_graph* g_host, const float* Z, const float* G,
                               const uint8_t* kstar, const float* w, const float* s, int K, int d,
-                              float beta, float one_minus_beta, float* dZ, float* r, float* hub_ws,
-                              float* const* r_peers, int n_peers, dl_stream_t stream);
+                              float beta, float one_minus_beta, float* dZ, float* r, float* x,
+                              int* x_valid_out, float* hub_ws, float* const* r_peers, int n_peers,
+                              dl_stream_t stream);
 int dl_pair_score_bwd_push(const dl_graph* inc_host, const int32_t* inc_pair, const float* Z,
                            const float* H, const float* dS, int K, int d, float T, float* dZ, float* dH,
                            float* hub_ws, float* const* dH_peers, int n_peers, dl_stream_t stream);

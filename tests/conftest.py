@@ -32,7 +32,8 @@ def load_golden(name):
     return g
 
 
-GRAPH_FIXTURES = [n for n in golden_names() if not n.startswith("module_")]
+# module_*: whole-module fixtures; *_graph: an edge list only (no reference outputs)
+GRAPH_FIXTURES = [n for n in golden_names() if not n.startswith("module_") and not n.endswith("_graph")]
 
 
 @pytest.fixture(scope="session")

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(syms)
     handle.dl_abi_version.restype = ctypes.c_int
-    assert handle.dl_abi_version() == 1
+    assert handle.dl_abi_version() == 2
     handle.dl_error_string.restype = ctypes.c_char_p
     assert b"symmetric" in handle.dl_error_string(-4)
     # size queries are pure host functions

@@ -323,7 +323,8 @@ def test_fused_exchange_kernels_write_every_peer(K, d):
     arr = (ctypes.c_void_p * 2)(*[p.data_ptr() for p in r_peers])
     dZ1, r1 = torch.zeros_like(Z), torch.empty_like(s)
     check(lib().dl_factor_bwd_gather_push(g.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d, 0.5, 0.5, ptr(dZ1),
-                                          ptr(r1), ptr(g.hub_scratch(K * d)), arr, 2, stream_of(dev)), "bwd gather push")
+                                          ptr(r1), None, None, ptr(g.hub_scratch(K * d)), arr, 2, stream_of(dev)),
+          "bwd gather push")
     assert torch.equal(dZ1, dZ_ref) and torch.equal(r1, r_ref)
     for p in r_peers:
         assert torch.equal(p, r_ref)

@@ -79,15 +79,17 @@ class OracleBackend:
         dS.copy_(torch.from_numpy(ds))
         return torch.tensor(loss, dtype=torch.float32)
 
-    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r):
+    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r, peers=None, x=None):
         lo, hi = g.part.lo, g.part.hi
         dz, rr = dZ.numpy().copy(), np.zeros(tuple(r.shape), np.float32)
         self.o.factor_bwd_gather(g.rowptr, g.col, Z.numpy(), G.numpy(), kstar[:g.nnz].numpy(),
                                  w[:g.nnz].numpy(), s.numpy(), beta, dz, rr)
         dZ[lo:hi] = torch.from_numpy(dz[lo:hi])
         r[lo:hi] = torch.from_numpy(rr[lo:hi])
+        return False                                   # x (per-entry dots for pass 2) not filled
 
-    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ, sj=None):
+    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ, sj=None, x=None):
+        assert x is None
         lo, hi = g.part.lo, g.part.hi
         dz = dZ.numpy().copy()
         self.o.factor_bwd_edges(g.rowptr, g.col, Z.numpy(), G.numpy(), s.numpy(), r.numpy(), beta, T, dz)
