@@ -25,6 +25,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# c5 keeps ~160 GB of 25.6-GB tensors live: let the caching allocator map segments instead of carving
+# fixed blocks, or fragmentation alone (26 GiB "reserved but unallocated") runs the device out of memory
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 WORKLOADS = {
     # BASELINE.json configs[4]: synthetic power-law graph 50M nodes / 500M edges, K=8, D=128, 100M pairs
@@ -437,7 +440,8 @@ def run_native(args):
                 upload((i + 1) % nb)                        # next step's input
             cur.wait_event(ready[slot])
             Zg = Zbufs[slot].requires_grad_(True)
-            loss, prob, _ = ops.link_bce_loss(Zg, g_full, batch, lab, wts, beta, T)
+            loss, prob, H = ops.link_bce_loss(Zg, g_full, batch, lab, wts, beta, T)
+            del H                                           # 25.6 GB the backward does not need
             loss.backward()
             free[slot].record(cur)
             prob_host.copy_(prob, non_blocking=True)
@@ -466,6 +470,9 @@ def run_native(args):
             del Zbufs[1:]
             nb = 1
             last.clear()
+            Zbufs[0].grad = None
+            Zbufs[0].requires_grad_(False)
+            torch.cuda.synchronize(dev)
             torch.cuda.empty_cache()
             e2e_run(max(args.warmup, 1), 0)
             t0 = time.perf_counter()

@@ -78,7 +78,9 @@ __device__ __forceinline__ float afl_dot(const float4 (&a)[C::C4], const float4 
 template <int K_, int d_>
 __global__ void __launch_bounds__(AflCfg<K_, d_>::THREADS, 1)
 k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __restrict__ kstar,
-          float* __restrict__ w, float* __restrict__ s, float* __restrict__ carry) {
+          float* __restrict__ w, float* __restrict__ s, float* __restrict__ carry, float2* __restrict__ kw_out) {
+  // kw_out != nullptr (symmetric attention, attn_sym.cu): g is the UPPER-triangle view of the graph; the
+  // routing of entry e goes to kw_out[e] = (w, kstar) as one 8-byte record and no row sums are made here
   using C = AflCfg<K_, d_>;
   constexpr int K = C::K, d = C::d, D = C::D, LPE = C::LPE, EPS = C::EPS, QPC = C::QPC, C4 = C::C4;
   constexpr int ROWS = C::ROWS, STAGE_B = C::STAGE_B;
@@ -110,14 +112,16 @@ k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __r
   DlChunkStream cs;
   cs.init(g.nnz, (long long)gridDim.x * C::NW);
 
+  // unconditional loads from a clamped index (a select against a default right after the load would
+  // make the warp wait for it at once); validity is applied in finish_meta, half a chunk later
   auto load_meta = [&](long long cc, AMeta& m) {
-    m.row = -1; m.col = 0; m.info = 0;
-    if (cc >= 0) {
-      const long long e = cc * DL_CH + lane;
-      if (e < g.nnz) { m.row = __ldg(g.erow + e); m.col = __ldg(g.col + e); }
-    }
+    const long long e = cc * DL_CH + lane;
+    const long long ec = (cc >= 0 && e < g.nnz) ? e : 0;
+    m.row = __ldg(g.erow + ec); m.col = __ldg(g.col + ec);
+    m.info = 0;
   };
-  auto finish_meta = [&](AMeta& m, int prow) {
+  auto finish_meta = [&](AMeta& m, long long cc, int prow) {
+    if (!(cc >= 0 && cc * DL_CH + lane < g.nnz)) m.row = -1;
     const int up = __shfl_up_sync(DL_FULL, m.row, EPS);
     const int wrap = __shfl_sync(DL_FULL, prow, (lane + 32 - EPS) & 31);
     const int prevE = lane >= EPS ? up : wrap;
@@ -166,7 +170,7 @@ k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __r
       for (int off = LPE; off < 32; off <<= 1) v = __fadd_rn(v, __shfl_xor_sync(DL_FULL, v, off));
       const bool to_head = first_run && head_open;
       const bool to_tail = !to_head && at_range_end && tail_open;
-      if (grp == 0 && factive) {
+      if (grp == 0 && factive && s != nullptr) {
         if (to_head || to_tail) carry[(cur_range * 2 + (to_tail ? 1 : 0)) * K + kap] = v;
         else {
           const float sv = (v == 0.0f) ? 1.0f : v;
@@ -185,7 +189,7 @@ k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __r
   long long c = cs.first(gw);
   AMeta mA, mB;
   load_meta(c, mA);
-  finish_meta(mA, -1);
+  finish_meta(mA, c, -1);
 #pragma unroll
   for (int pq = 0; pq < AFL_RING - 1; ++pq) {
     issue_stage(ring + pq * STAGE_B, mA, pq);
@@ -208,7 +212,7 @@ k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __r
 
 #pragma unroll 1
     for (int q = 0; q < QPC; ++q) {
-      if (q == QPC / 2) finish_meta(mB, mA.row);
+      if (q == QPC / 2) finish_meta(mB, cn, mA.row);
       int islot = rslot + (AFL_RING - 1);
       if (islot >= AFL_RING) islot -= AFL_RING;
       const unsigned ist = ring + islot * STAGE_B;
@@ -262,8 +266,12 @@ k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __r
         const float wv = __shfl_sync(DL_FULL, a, gbase + ks);
         if (valid && kap == 0) {
           const long long e = c * DL_CH + src;
-          kstar[e] = (unsigned char)ks;
-          w[e] = wv;
+          if (kw_out) {
+            kw_out[e] = make_float2(wv, __int_as_float(ks));
+          } else {
+            kstar[e] = (unsigned char)ks;
+            w[e] = wv;
+          }
         }
         const float contrib = (valid && kap == ks) ? wv : 0.0f;
         // row sums: the whole stage continues the current row (common), or run by run
@@ -294,7 +302,7 @@ k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __r
 template <int K_, int d_>
 struct AflLaunch {
   static int run(const DlGraphDev& g, const float* Z, float T, unsigned char* kstar, float* w, float* s,
-                 float* carry, cudaStream_t st) {
+                 float* carry, float2* kw_out, cudaStream_t st) {
     using C = AflCfg<K_, d_>;
     int dev = 0, sms = 0;
     DL_CUDA_TRY(cudaGetDevice(&dev));
@@ -306,7 +314,7 @@ struct AflLaunch {
     long long grid = (n_ranges + C::NW - 1) / C::NW;
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
-    k_attn_fl<K_, d_><<<(int)grid, C::THREADS, C::SMEM, st>>>(g, Z, T, kstar, w, s, carry);
+    k_attn_fl<K_, d_><<<(int)grid, C::THREADS, C::SMEM, st>>>(g, Z, T, kstar, w, s, carry, kw_out);
     DL_LAUNCH_CHECK();
     return DL_OK;
   }
@@ -314,18 +322,29 @@ struct AflLaunch {
 
 }  // namespace
 
-// returns -1000 when (K, d) has no factor-per-lane instantiation; scratch: 3 * n_ranges * K floats
+// returns -1000 when (K, d) has no factor-per-lane instantiation; scratch: 3 * n_ranges * K floats.
+// kw_out != nullptr: packed (w, kstar) records, no row sums (kstar, w, s, scratch may be null)
 int dl_launch_attn_fl(const DlGraphDev& g, const float* Z, int K, int d, float T, unsigned char* kstar,
-                      float* w, float* s, float* scratch, cudaStream_t st) {
-  if (!g.erow || g.nnz == 0 || !scratch) return -1000;
+                      float* w, float* s, float* scratch, cudaStream_t st, float2* kw_out) {
+  if (!g.erow || g.nnz == 0 || (!scratch && !kw_out)) return -1000;
+  if (kw_out) s = nullptr;
   int rc = -1000;
-  if (K == 8 && d == 16) rc = AflLaunch<8, 16>::run(g, Z, T, kstar, w, s, scratch, st);
-  else if (K == 8 && d == 8) rc = AflLaunch<8, 8>::run(g, Z, T, kstar, w, s, scratch, st);
-  else if (K == 5 && d == 16) rc = AflLaunch<5, 16>::run(g, Z, T, kstar, w, s, scratch, st);
-  else if (K == 5 && d == 32) rc = AflLaunch<5, 32>::run(g, Z, T, kstar, w, s, scratch, st);
-  else if (K == 3 && d == 32) rc = AflLaunch<3, 32>::run(g, Z, T, kstar, w, s, scratch, st);
-  else if (K == 4 && d == 32) rc = AflLaunch<4, 32>::run(g, Z, T, kstar, w, s, scratch, st);
-  else if (K == 8 && d == 32) rc = AflLaunch<8, 32>::run(g, Z, T, kstar, w, s, scratch, st);
+#define AFL_CASE(KK, DD) \
+  if (K == KK && d == DD) rc = AflLaunch<KK, DD>::run(g, Z, T, kstar, w, s, scratch, kw_out, st);
+  AFL_CASE(8, 16)
+  AFL_CASE(8, 8)
+  AFL_CASE(5, 16)
+  AFL_CASE(5, 32)
+  AFL_CASE(3, 32)
+  AFL_CASE(4, 32)
+  AFL_CASE(8, 32)
+#undef AFL_CASE
   if (rc != DL_OK) return rc;
+  if (kw_out) return DL_OK;
   return dl_gather_chain_rowsum(g, K, scratch, s, st);
+}
+
+bool dl_attn_fl_has(int K, int d) {
+  return (K == 8 && (d == 16 || d == 8 || d == 32)) || (K == 5 && (d == 16 || d == 32)) || (K == 3 && d == 32) ||
+         (K == 4 && d == 32);
 }

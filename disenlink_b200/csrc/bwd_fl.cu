@@ -119,21 +119,23 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
   DlChunkStream cs;
   cs.init(g.nnz, (long long)gridDim.x * C::NW);
 
+  // Unconditional loads from a clamped index: a select between a default and the loaded value right
+  // here would make the warp wait for the loads at once (ncu: the FSEL / spill store after these loads
+  // held 14 % of all stall samples); validity is applied in finish_meta, half a chunk later.
+  const float* sjp = sj ? sj : reinterpret_cast<const float*>(g.erow);
   auto load_meta = [&](long long cc, FMeta& m) {
-    m.row = -1; m.col = 0; m.info = 0; m.sj = 1.0f; m.rj = 0.0f; m.xv = 0.0f;
-    if (cc >= 0) {
-      const long long e = cc * DL_CH + lane;
-      if (e < g.nnz) {
-        m.row = __ldg(g.erow + e); m.col = __ldg(g.col + e); m.info = __ldg(kstar + e);
-        if (sj) m.sj = __ldg(sj + e);        // s[col, kstar] as the forward saw it: no gather needed
-        if (HAS_X) m.xv = __ldg(xc + e);     // <G[col,kstar], Z[row,kstar]> as pass 1 computed it
-      }
-    }
+    const long long e = cc * DL_CH + lane;
+    const long long ec = (cc >= 0 && e < g.nnz) ? e : 0;
+    m.row = __ldg(g.erow + ec); m.col = __ldg(g.col + ec); m.info = __ldg(kstar + ec);
+    m.sj = __ldg(sjp + ec);                  // s[col, kstar] as the forward saw it: no gather needed
+    if (HAS_X) m.xv = __ldg(xc + ec);        // <G[col,kstar], Z[row,kstar]> as pass 1 computed it
+    m.rj = 0.0f;
   };
   // second half of a chunk's metadata, once row / col / kstar have arrived: the s[j,k], r[j,k]
   // gathers and the own-row bookkeeping (prow = per-lane rows of the previous chunk of this warp)
-  auto finish_meta = [&](FMeta& m, int prow) {
+  auto finish_meta = [&](FMeta& m, long long cc, int prow) {
     const int ks = m.info;
+    if (!(cc >= 0 && cc * DL_CH + lane < g.nnz)) { m.row = -1; m.sj = 1.0f; }
     if (m.row >= 0) {
       if (sr) {                 // (s, r) interleaved per (node, factor): one 8-byte gather for both
         const float2 v = __ldg(sr + (long long)m.col * K + ks);
@@ -241,7 +243,7 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
   long long c = cs.first(gw);
   FMeta mA, mB;
   load_meta(c, mA);
-  finish_meta(mA, -1);
+  finish_meta(mA, c, -1);
 #pragma unroll
   for (int pq = 0; pq < FL_RING - 1; ++pq) {
     issue_stage(ring + pq * STAGE_B, mA, pq);
@@ -267,7 +269,7 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
 
 #pragma unroll 1
     for (int q = 0; q < QPC; ++q) {
-      if (q == QPC / 2) finish_meta(mB, mA.row);
+      if (q == QPC / 2) finish_meta(mB, cn, mA.row);
       int islot = rslot + (FL_RING - 1);
       if (islot >= FL_RING) islot -= FL_RING;
       const unsigned ist = ring + islot * STAGE_B;

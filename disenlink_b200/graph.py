@@ -27,6 +27,10 @@ class Graph:
     warp owns more than one segment.
     """
 
+    # below this many entries the attention runs two-sided: the graph fits L2 and the extra launches
+    # of the symmetric path cost more than the row gathers it saves
+    SYM_MIN_NNZ = 1 << 20
+
     def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, n_nodes: int, row_base: int = 0,
                  n_global: int = None):
         require_cuda(rowptr, "rowptr")
@@ -39,6 +43,8 @@ class Graph:
         self.col = col.contiguous()
         self.nnz = int(col.numel())
         self._rev = None
+        self._sym = None                      # (upper Graph, eidx) | False (pattern not symmetric / unavailable)
+        self.sym_min_nnz = self.SYM_MIN_NNZ
         self._flags = _lib.default_flags()
         self._build_items()
 
@@ -182,7 +188,43 @@ class Graph:
         return self._rev
 
     def assert_symmetric(self) -> None:
-        self.rev_index()
+        """Raises DlError(DL_EASYM) unless every entry (i,j) has its mirror (j,i); checked once."""
+        if self._sym is None and self._rev is None:
+            if self.row_base == 0 and self.n_global == self.N and self.nnz < 2**31 - 1:
+                self.sym_view()
+            else:
+                self.rev_index()
+        if self._sym is False and self._rev is None:
+            self.rev_index()                   # raises with the library's message
+
+    def sym_view(self):
+        """-> (upper-triangle Graph, eidx int32 [nnz]) for the symmetric attention
+        (dl_edge_attn_fwd_sym), or None when the pattern is not symmetric, the graph is
+        row-partitioned or has >= 2^31 entries.  Integer work on the device, done once and cached."""
+        if self._sym is None:
+            self._sym = False
+            if self.row_base == 0 and self.n_global == self.N and 0 < self.nnz < 2**31 - 1:
+                L, dev, N = lib(), self.device, self.N
+                with torch.cuda.device(dev):
+                    ws_bytes = L.dl_sym_index_workspace_bytes(N)
+                    ws = _ws(ws_bytes, dev)
+                    uptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
+                    status = torch.zeros(1, dtype=torch.int32, device=dev)
+                    check(L.dl_sym_index(ptr(self.rowptr), ptr(self.col), ptr(self.erow), N, self.nnz, ptr(uptr),
+                                         None, None, None, ptr(ws), ws_bytes, stream_of(dev)), "dl_sym_index(count)")
+                    nnz_u = int(uptr[-1].item())
+                    ucol = torch.empty(max(nnz_u, 1), dtype=torch.int32, device=dev)
+                    eidx = torch.empty(self.nnz, dtype=torch.int32, device=dev)
+                    check(L.dl_sym_index(ptr(self.rowptr), ptr(self.col), ptr(self.erow), N, self.nnz, ptr(uptr),
+                                         ptr(ucol), ptr(eidx), ptr(status), ptr(ws), ws_bytes, stream_of(dev)),
+                          "dl_sym_index(fill)")
+                    ok = int(status.item()) == 0
+                    del ws
+                if ok:
+                    upper = Graph(uptr, ucol[:nnz_u], N)
+                    upper._sym = False
+                    self._sym = (upper, eidx)
+        return self._sym or None
 
     def rows(self) -> torch.Tensor:
         """Row id of every entry (torch op; for tests and dense views)."""

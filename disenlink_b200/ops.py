@@ -51,8 +51,22 @@ def edge_attn_fwd(graph: Graph, Z: torch.Tensor, T: float = 1.0, out=None):
             kstar = torch.empty(max(graph.nnz, 1), dtype=torch.uint8, device=dev)
             w = torch.empty(max(graph.nnz, 1), dtype=torch.float32, device=dev)
             s = torch.empty(graph.n_global, K, dtype=torch.float32, device=dev)
-        check(lib().dl_edge_attn_fwd(graph.ref, ptr(Z), K, d, float(T), ptr(kstar), ptr(w), ptr(s),
-                                     ptr(graph.hub_scratch(K)), stream_of(dev)), "dl_edge_attn_fwd")
+        rc = _lib.DL_EUNSUPPORTED
+        sym = None
+        if graph.nnz >= graph.sym_min_nnz and not (graph.flags & (_lib.DL_F_NO_SYM | _lib.DL_F_NO_STREAM |
+                                                                  _lib.DL_F_NO_FL | _lib.DL_F_NO_FL_ATTN)):
+            sym = graph.sym_view()              # None: not symmetric / row-partitioned
+        if sym is not None:
+            # every undirected edge once: rows are gathered for the upper-triangle entries only
+            upper, eidx = sym
+            kw = _x_scratch(graph, 2 * upper.nnz)
+            rc = lib().dl_edge_attn_fwd_sym(graph.ref, upper.ref, ptr(eidx), ptr(Z), K, d, float(T), ptr(kstar),
+                                            ptr(w), ptr(s), ptr(graph.hub_scratch(K)), ptr(kw), stream_of(dev))
+            if rc != _lib.DL_EUNSUPPORTED:
+                check(rc, "dl_edge_attn_fwd_sym")
+        if rc == _lib.DL_EUNSUPPORTED:
+            check(lib().dl_edge_attn_fwd(graph.ref, ptr(Z), K, d, float(T), ptr(kstar), ptr(w), ptr(s),
+                                         ptr(graph.hub_scratch(K)), stream_of(dev)), "dl_edge_attn_fwd")
     return kstar[:graph.nnz], w[:graph.nnz], s
 
 
@@ -79,12 +93,14 @@ def factor_spmm_fwd(graph: Graph, Z, kstar, w, s, beta: float, out=None, sj=None
     return H
 
 
-def _x_scratch(graph: Graph):
-    """[nnz] scratch in which pass 1 leaves <G[j,k*], Z[i,k*]> per entry for pass 2 -- cached on the
-    graph handle."""
+def _x_scratch(graph: Graph, n_floats: int = 0):
+    """Per-entry fp32 scratch cached on the graph handle: pass 1 of the backward leaves
+    <G[j,k*], Z[i,k*]> per entry there for pass 2 (nnz floats); the symmetric attention keeps its
+    packed (w, kstar) records of the upper-triangle entries there during the forward (2 nnz_u floats)."""
+    need = max(graph.nnz, int(n_floats), 1)
     buf = getattr(graph, "_x_scratch", None)
-    if buf is None or buf.numel() < max(graph.nnz, 1):
-        buf = torch.empty(max(graph.nnz, 1), dtype=torch.float32, device=graph.device)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.float32, device=graph.device)
         graph._x_scratch = buf
     return buf
 
@@ -264,6 +280,9 @@ class _FactorAggregate(torch.autograd.Function):
     @staticmethod
     def backward(ctx, G, _gk, _gw, _gs):
         Z, kstar, w, s = ctx.saved_tensors
+        # the gather-only backward collects the (j,i) terms from row i's side: it needs a symmetric
+        # pattern (always true for adj_sym, main_disentangled.py:141-142).  Checked once per graph.
+        ctx.graph.assert_symmetric()
         dZ, _ = factor_bwd(ctx.graph, Z, G.contiguous(), kstar, w, s, ctx.beta, ctx.T, sj=ctx.sj)
         return dZ, None, None, None
 
@@ -391,7 +410,9 @@ class _LinkBCELoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Z, graph, batch, labels, weights, beta, T):
         Zc = Z.detach().contiguous()
-        need_grad = ctx.needs_input_grad[0]
+        need_grad = ctx.needs_input_grad[0]        # False under torch.no_grad(): the eager backward is skipped
+        if need_grad:
+            graph.assert_symmetric()          # gather-only backward (see _FactorAggregate.backward)
         kstar, w, s = edge_attn_fwd(graph, Zc, T)
         sj, zs = _spmm_side_buffers(graph, Zc, need_grad)
         H = factor_spmm_fwd(graph, Zc, kstar, w, s, beta, sj=sj, zs=zs)
@@ -410,7 +431,9 @@ class _LinkBCELoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss, _gp, _gh):
         (dZ,) = ctx.saved_tensors
-        return dZ.mul_(gloss), None, None, None, None, None, None   # in place: dZ is this op's own buffer
+        # out of place: a second backward through the same graph (retain_graph, accumulation) must see
+        # the unscaled dZ again, and the returned gradient must not alias a saved tensor
+        return dZ * gloss, None, None, None, None, None, None
 
 
 def link_bce_loss(Z, graph: Graph, batch: PairBatch, labels, weights, beta: float, T: float = 1.0):

@@ -239,6 +239,9 @@ class CudaBackend:
         inc = self.Graph(inc_ptr, inc_other, part.n_local, row_base=part.lo, n_global=part.n_pad)
         return shard, inc, inc_pair
 
+    def entry_scratch(self, g):
+        return self.ops._x_scratch(g)
+
     # -- kernels (all write only the owned rows of the full-size outputs) --
     def edge_attn_fwd(self, g, Z, T, kstar, w, s, peers=None):
         if peers is None:
@@ -328,7 +331,9 @@ class PartitionedLinkStep:
         # during the forward); several ranks: s[col, kstar] per local entry goes forward -> pass 2
         self.prescale = (part.world == 1) and not (getattr(self.graph, "flags", 0) & 8)    # _lib.DL_F_NO_PRESCALE
         self.sj = None if self.prescale else torch.empty(max(nnz, 1), **f32)
-        self.x = torch.empty(max(nnz, 1), **f32)   # <G[j,k*], Z[i,k*]> per entry: pass 1 -> pass 2
+        # <G[j,k*], Z[i,k*]> per entry, pass 1 -> pass 2 (the graph's per-entry scratch, shared with the
+        # symmetric attention's packed records, which are dead by then)
+        self.x = self.be.entry_scratch(self.graph) if hasattr(self.be, "entry_scratch") else None
         self.s = torch.ones(part.n_pad, K, **f32)
         self.r = torch.zeros(part.n_pad, K, **f32)
         self.H = torch.zeros(part.n_pad, K, d, **f32)

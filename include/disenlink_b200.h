@@ -132,6 +132,8 @@ typedef struct dl_graph {
 #define DL_F_NO_SR 32u        /* backward pass 2 gathers s and r separately instead of packed (s, r) */
 #define DL_F_NO_XDOT 64u      /* backward pass 2 re-gathers the G[j,kstar] slice instead of reading the
                                  per-entry dot pass 1 left in x */
+#define DL_F_NO_SYM 128u      /* (host side) attention evaluates both directions of every edge even when
+                                 the symmetric path (dl_edge_attn_fwd_sym) is available */
 
 /* ------------------------------------------------------------------------------------------
  * (2) per-edge K-factor attention with hard routing.
@@ -143,6 +145,30 @@ size_t dl_hub_scratch_floats(const dl_graph* g_host, int64_t width);
 
 int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float T,
                      uint8_t* kstar, float* w, float* s, float* hub_ws, dl_stream_t stream);
+
+/* (2s) the same, evaluating every undirected edge ONCE.  q_k(i,j) is symmetric and so are, bit for bit,
+ * kstar and w (canonical arithmetic), so for a symmetric adjacency that is not row-partitioned the
+ * 512-byte row gather is only needed for the entries with col >= row:
+ *   dl_sym_index  (integer, once per graph; two calls like dl_hub_items)
+ *       call 1 (ucol == NULL): uptr [N+1] (device int64) = row pointers of the upper-triangle view;
+ *                              the caller reads uptr[N] = nnz_u to size ucol;
+ *       call 2: ucol [nnz_u] = its columns, eidx [nnz] = for every entry of the full CSR the position
+ *               in the upper view of itself (col >= row) or of its mirror (col < row);
+ *               status_out (device int32) = DL_EASYM if some entry has no mirror.
+ *       erow = dl_entry_rows of the full CSR.  nnz < 2^31.  ws: dl_sym_index_workspace_bytes(N).
+ *   dl_edge_attn_fwd_sym: upper_host = a dl_graph over (uptr, ucol) with its own erow; the factor-per-lane
+ *       attention kernel runs on it and leaves packed (w, kstar) records in kw_scratch (2 * nnz_u floats);
+ *       a streaming pass expands them through eidx into kstar / w of the full CSR and makes the row
+ *       sums s.  Outputs are identical to dl_edge_attn_fwd (kstar, w bit for bit; s up to the order of
+ *       the fp32 row sums).  hub_ws: dl_hub_scratch_floats(g, K) floats.  DL_EUNSUPPORTED when (K, d) has
+ *       no factor-per-lane instantiation: call dl_edge_attn_fwd instead.  [ref: model.py:56-73] */
+size_t dl_sym_index_workspace_bytes(int64_t N);
+int dl_sym_index(const int64_t* rowptr, const int32_t* col, const int32_t* erow, int64_t N, int64_t nnz,
+                 int64_t* uptr, int32_t* ucol, int32_t* eidx, int32_t* status_out, void* ws, size_t ws_bytes,
+                 dl_stream_t stream);
+int dl_edge_attn_fwd_sym(const dl_graph* g_host, const dl_graph* upper_host, const int32_t* eidx, const float* Z,
+                         int K, int d, float T, uint8_t* kstar, float* w, float* s, float* hub_ws,
+                         float* kw_scratch, dl_stream_t stream);
 
 /* (3) per-factor gather / segment-sum aggregation with the beta residual.
  * [ref: model.py:75]  H[i,k] = beta Z[i,k] + (1-beta) sum_{j: kstar(i,j)=k} w_ij / s[j,k] Z[j,k]

@@ -330,3 +330,63 @@ def test_large_graph_properties(dl):
     b = ops.pair_score_fwd(Z, H, ops.PairBatch(pv, pu, n), 1.0)[0]
     assert torch.equal(a, b)
     assert torch.isfinite(H).all() and torch.isfinite(a).all()
+
+
+# ------------------------------------------------------------------------------------------
+# symmetric attention (every undirected edge once) and the asymmetric-adjacency guard
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K,d", [(8, 16), (5, 32), (8, 8), (3, 32), (10, 32)])
+def test_symmetric_attention_equals_two_sided(dl, oracle, K, d):
+    """dl_edge_attn_fwd_sym: kstar / w bit-identical to the two-sided kernel and to the oracle, s
+    within the summation-order tolerance; shapes without a factor-per-lane kernel fall back."""
+    ops, Graph = dl
+    from disenlink_b200 import _lib
+    rng = np.random.default_rng(K * 7 + d)
+    n = 30000
+    src, dst = random_graph(rng, n, 200000, hubs=((3, 9000), (77, 600)))
+    Z = (rng.standard_normal((n, K, d)) * (0.8 / np.sqrt(np.sqrt(d)))).astype(np.float32)
+    g = Graph.from_edges(t(src), t(dst), n)
+    g.sym_min_nnz = 0
+    upper, eidx = g.sym_view()
+    rowptr, col = oracle.csr_from_edges(src, dst, n)
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    up = col >= rows
+    assert upper.nnz == int(up.sum())
+    assert np.array_equal(upper.col.cpu().numpy(), col[up])
+    assert np.array_equal(upper.rowptr.cpu().numpy(), np.concatenate([[0], np.cumsum(np.bincount(rows[up], minlength=n))]))
+    # eidx: own position for upper entries, the mirror's for lower ones
+    ukey = rows[up].astype(np.int64) * n + col[up]
+    key = np.where(up, rows.astype(np.int64) * n + col, col.astype(np.int64) * n + rows)
+    assert np.array_equal(eidx.cpu().numpy(), np.searchsorted(ukey, key))
+    k1, w1, s1 = (x.clone() for x in ops.edge_attn_fwd(g, t(Z), 1.0))
+    g.flags = _lib.DL_F_NO_SYM
+    k0, w0, s0 = ops.edge_attn_fwd(g, t(Z), 1.0)
+    assert torch.equal(k0, k1) and torch.equal(w0, w1)
+    assert relerr(s1.cpu().numpy(), s0.cpu().numpy()) < ORA_TOL
+    o_k, o_w, o_s = oracle.edge_attn_fwd(rowptr, col, Z, 1.0)
+    assert np.array_equal(k1.cpu().numpy(), o_k)
+    assert np.array_equal(w1.cpu().numpy().view(np.uint32), o_w.view(np.uint32))
+    assert relerr(s1.cpu().numpy(), o_s) < ORA_TOL
+
+
+def test_asymmetric_adjacency_forward_ok_backward_refuses(dl, oracle):
+    """Disentangle.forward(x, adj) accepts any adj; the gather-only backward needs a symmetric
+    pattern and must say so instead of returning wrong gradients."""
+    ops, Graph = dl
+    from disenlink_b200._lib import DlError
+    rng = np.random.default_rng(2)
+    n, K, d = 300, 3, 8
+    a = (rng.random((n, n)) < 0.03).astype(np.float32)          # NOT symmetrised
+    g = Graph.from_dense(t(a))
+    g.sym_min_nnz = 0
+    assert g.sym_view() is None
+    Z = (rng.standard_normal((n, K, d)) * 0.5).astype(np.float32)
+    r, c = np.nonzero(a)
+    rowptr = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=n))]).astype(np.int64)
+    o_H, o_k, o_w, o_s = oracle.factor_fwd(rowptr, c.astype(np.int32), Z, 0.7, 1.0)
+    Zt = t(Z).requires_grad_(True)
+    H, kstar, w, s = ops.factor_aggregate(Zt, g, 0.7, 1.0, return_attention=True)
+    assert np.array_equal(kstar.cpu().numpy(), o_k)
+    assert relerr(H.detach().cpu().numpy(), o_H) < ORA_TOL
+    with pytest.raises(DlError, match="symmetric"):
+        H.sum().backward()

@@ -39,10 +39,11 @@ def power_law_edges(N, E, seed=0):
 
 SCALE_CASES = [
     # (N, E directed, K, d)            C4 = snap-patents scale
-    (2_923_922, 13_975_788, 8, 16),   # headline shape class (factor-per-lane kernels)
-    (2_923_922, 13_975_788, 5, 32),   # tuned chameleon shape (hyperparameters_setting:2)
-    (2_923_922, 13_975_788, 8, 8),    # Pubmed D = 64
-    (1_000_000, 5_000_000, 8, 64),    # Pubmed D = 512 (row = 2 KB; smaller N keeps the oracle in seconds)
+    (2_923_922, 13_975_788, 8, 16),   # headline shape class (factor-per-lane kernels), full C4 size
+    (1_000_000, 5_000_000, 5, 32),    # tuned chameleon shape (hyperparameters_setting:2)
+    (1_000_000, 5_000_000, 8, 8),     # Pubmed D = 64
+    (500_000, 2_500_000, 8, 64),      # Pubmed D = 512 (row = 2 KB)
+    # (smaller N for the other shape classes keeps the oracle side of the whole file under two minutes)
 ]
 
 
@@ -53,18 +54,24 @@ def test_scale_parity_vs_oracle(dl, oracle, N, E, K, d):
     src, dst = power_law_edges(N, E)
     rng = np.random.default_rng(K * 100 + d)
     Z = (rng.standard_normal((N, K, d), dtype=np.float32) * np.float32(d ** -0.25))
-    P = 2_000_000
+    P = min(2_000_000, E // 4)
     e = rng.integers(0, E, P // 6)
     pu = np.concatenate([src[e], np.repeat(src[e], 5)])
     pv = np.concatenate([dst[e], rng.integers(0, N, 5 * e.size)])
     order = np.argsort(pu, kind="stable")
     pu, pv = pu[order], pv[order]
     res, g = run_all(ops, Graph, oracle, src, dst, N, Z, 0.5, 1.0, pu, pv)
-    assert g.nnz > 1.9 * E * 0.95
+    assert g.nnz > 1.8 * E
     assert g.n_hub > 0
     errs = {k: relerr(*v) for k, v in res.items() if k not in ("kstar", "w")}
     print("scale parity N=%d K=%d d=%d nnz=%d max degree=%d rel-err vs oracle: %s" % (
         N, K, d, g.nnz, int(g.degrees().max()), {k: "%.2e" % e for k, e in errs.items()}))
+    # prob = sigmoid(logit): its error is the logit's ABSOLUTE error (x <= 1/4), and the largest logits
+    # here are in the hundreds, so prob is checked through that bound rather than against its own max
+    pg, po = res.pop("prob")
+    lg, lo = res["logit"]
+    assert np.abs(pg - po).max() <= 0.25 * np.abs(lg.astype(np.float64) - lo).max() + 2e-7
+    res["prob"] = (po, po)
     assert_matches_oracle(res, tol=1e-5)
 
 
