@@ -43,7 +43,8 @@ WORKLOADS = {
     "tiny": dict(N=200_000, E=2_000_000, K=8, d=16, P=400_000, beta=0.5, T=1.0,
                  name="synthetic power-law 200k nodes / 2M directed edges (smoke)"),
 }
-CPU_SAMPLE = dict(N=500_000, E=5_000_000, P=1_000_000)   # 1/100 of c5, same generator
+CPU_SAMPLE = dict(N=5_000_000, E=50_000_000, P=10_000_000)   # 1/10 of c5 (= the "mid" workload), same generator:
+#                                                              ~20 s of oracle time on 16 host threads, ~15 GB of host RAM
 M_NEG = 5
 POWER = 3.0   # endpoint rank ~ N * U^3  ->  degree(rank) ~ rank^(-2/3), degree exponent alpha = 2.5
 
@@ -167,6 +168,99 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port on a bounded sample (all host threads)
 # ------------------------------------------------------------------------------------------------
+def dense_reference_leg(device=None):
+    """The reference's OWN dense path (baseline/_ref/model.py, unmodified, staged by
+    tools/stage_reference.sh) timed on the host cores on the configs it can run -- chameleon
+    (hyperparameters_setting:2: K=5, nhid=512, d=32, beta=.7) and Cora (argparse defaults: K=3,
+    nhid=512, d=32, beta=.9) -- next to this repository's module on the same x / adj_sym / weights on
+    the GPU: model(x, adj_sym) forward and forward + backward of a BCE over all N^2 scores
+    (model.py:105-114).  3 warm-up + 5 timed calls, median."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "model.py")):
+        return {"unavailable": "baseline/_ref/model.py not staged (tools/stage_reference.sh needs /root/reference)"}
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_model", os.path.join(ref_dir, "model.py"))
+    refmodel = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(refmodel)
+    from disenlink_b200 import data as dl_data
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    out = {"cores": threads, "what": "model(x, adj_sym) of the unmodified reference model.py on the host cores vs "
+                                     "disenlink_b200.model.Disentangle on the same inputs on the GPU; 3 warm-up + 5 timed, median"}
+    cases = []
+    cham = os.path.join(ref_dir, "data_pre_false", "chameleon", "raw", "chameleon.npz")
+    if os.path.exists(cham):
+        x, ei, _ = dl_data.read_wikipedia_npz(cham)
+        cases.append(("chameleon_K5_d32", dl_data.row_standardize(x), ei, dict(nhid=512, d=32, K=5, beta=0.7)))
+    cora = os.path.join(ref_dir, "data", "cora", "raw")
+    if os.path.exists(cora):
+        x, ei, _ = dl_data.read_planetoid(cora, "cora")
+        cases.append(("cora_K3_d32", x, ei, dict(nhid=512, d=32, K=3, beta=0.9)))
+
+    def timed(fn, sync=None, warm=3, reps=5):
+        ts = []
+        for i in range(warm + reps):
+            if sync:
+                sync()
+            t0 = time.perf_counter()
+            fn()
+            if sync:
+                sync()
+            if i >= warm:
+                ts.append(time.perf_counter() - t0)
+        return sorted(ts)[len(ts) // 2]
+
+    for name, x, ei, hp in cases:
+        n = x.shape[0]
+        tr = dl_data.split_edges(ei.shape[1], seed=0)[0]            # main_disentangled.py:134-142
+        adj = torch.zeros(n, n)
+        adj[ei[0][tr], ei[1][tr]] = 1
+        adj_sym = ((adj + adj.t()) != 0).float()
+        nnz = int(adj_sym.sum().item())
+        torch.manual_seed(0)
+        ref = refmodel.Disentangle(x.shape[1], hp["nhid"], hp["d"], nfactor=hp["K"], beta=hp["beta"], t=1)
+
+        def ref_fwd():
+            with torch.no_grad():
+                ref(x, adj_sym)
+
+        def ref_fwd_bwd():
+            ref.zero_grad()
+            _, a = ref(x, adj_sym)
+            F.binary_cross_entropy(a, adj_sym).backward()
+        rec = {"N": n, "nnz_sym": nnz, **hp, "ref_cpu_fwd_ms": 1e3 * timed(ref_fwd), "ref_cpu_fwd_bwd_ms": 1e3 * timed(ref_fwd_bwd)}
+        rec["ref_cpu_edges_per_s"] = nnz / (rec["ref_cpu_fwd_bwd_ms"] * 1e-3)
+        if device is not None:
+            from disenlink_b200.model import Disentangle
+            ours = Disentangle(x.shape[1], hp["nhid"], hp["d"], nfactor=hp["K"], beta=hp["beta"], t=1)
+            ours.load_state_dict(ref.state_dict(), strict=True)
+            ours = ours.to(device)
+            xg, ag = x.to(device), adj_sym.to(device)
+            sync = lambda: torch.cuda.synchronize(device)
+
+            def our_fwd():
+                with torch.no_grad():
+                    ours(xg, ag)
+
+            def our_fwd_bwd():
+                ours.zero_grad()
+                _, a = ours(xg, ag)
+                F.binary_cross_entropy(a, ag).backward()
+            rec["gpu_fwd_ms"] = 1e3 * timed(our_fwd, sync)
+            rec["gpu_fwd_bwd_ms"] = 1e3 * timed(our_fwd_bwd, sync)
+            rec["gpu_edges_per_s"] = nnz / (rec["gpu_fwd_bwd_ms"] * 1e-3)
+            with torch.no_grad():
+                Hr, ar = ref(x, adj_sym)
+                Ho, ao = ours(xg, ag)
+            rec["max_abs_diff_link_pred"] = float((ao.cpu() - ar).abs().max())
+            rec["max_rel_diff_H"] = float((Ho.cpu() - Hr).abs().max() / Hr.abs().max())
+        out[name] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in rec.items()}
+    return out
+
+
 def cpu_baseline(K, d, beta, T, steps=2, warmup=1):
     import numpy as np
     import torch
@@ -201,15 +295,16 @@ def cpu_baseline(K, d, beta, T, steps=2, warmup=1):
     return {"value": nnz / tf, "unit": "edges/s", "cores": threads, "kind": "port",
             "pair_scores_per_s": cs["P"] / (sum(t_pair_fwd) / len(t_pair_fwd)),
             "ms_per_step": 1e3 * sum(t_all) / len(t_all),
-            "sample": f"same power-law generator at 1/100 scale: N={cs['N']}, E={cs['E']} directed edges "
+            "sample": f"same power-law generator at 1/10 scale: N={cs['N']}, E={cs['E']} directed edges "
                       f"(nnz={nnz}), P={cs['P']} pairs, K={K}, d={d}; {steps} timed steps after {warmup} "
                       f"warm-up; C oracle (oracle/disen_oracle.c, OpenMP, {threads} threads)"}
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU math.  The dense model.py path needs
-    (9K+6) N^2 4 bytes (121 GB already at N = 19 717) and /root/reference does not exist on the GPU
-    box, so this arm times the oracle port of the same math, all host threads, bounded sample."""
+    (9K+6) N^2 4 bytes (121 GB already at N = 19 717), so on this arm's config it is the oracle port of
+    the same math that is timed -- all host threads, bounded sample (1/10 scale); the unmodified dense
+    model.py itself is timed where it can run (chameleon, Cora) and reported under "dense_reference"."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -223,9 +318,114 @@ def run_reference(args):
             "pair_scores_per_s": cb["pair_scores_per_s"],
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "edges/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+                    "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "dense_reference": dense_reference_leg(None)}
     print(json.dumps(line), flush=True)
 
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE.json configs, measured the same way (device-timed phases, one GPU)
+# ------------------------------------------------------------------------------------------------
+def measure_config(name, src, dst, N, K, d, beta, dev, peak, steps=10, warmup=3, P=None, note=""):
+    """One BASELINE config through the same PartitionedLinkStep as the headline workload (world = 1):
+    -> {nnz, value (edges/s fwd+bwd), ms per phase, HBM roofline fraction on SURVEY's bytes}."""
+    import torch
+    from disenlink_b200.partition import PartitionedLinkStep
+    E = int(src.numel())
+    g = torch.Generator(device=dev).manual_seed(1)
+    P_pos = max((P or min(E, 4_000_000)) // (1 + M_NEG), 1)
+    e = torch.randint(0, E, (P_pos,), generator=g, device=dev)
+    pu, pv = src[e], dst[e]
+    u = torch.cat([pu, pu.repeat(M_NEG)])
+    v = torch.cat([pv, torch.randint(0, N, (P_pos * M_NEG,), generator=g, device=dev)])
+    lab = torch.cat([torch.ones(P_pos, device=dev), torch.zeros(P_pos * M_NEG, device=dev)])
+    wts = torch.cat([torch.full((P_pos,), 1.0 / P_pos, device=dev),
+                     torch.full((P_pos * M_NEG,), 1.0 / (M_NEG * P_pos * M_NEG), device=dev)])
+    order = torch.sort(u, stable=True).indices
+    u, v, lab, wts = u[order], v[order], lab[order], wts[order]
+    events = []
+
+    def mark(nm):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(dev))
+        events.append((nm, ev))
+    step = PartitionedLinkStep(src, dst, N, u, v, lab, wts, K, d, beta, 1.0, world=1, rank=0, device=dev, mark=mark)
+    Z = gen_Z(step.part.n_pad, K, d, 0, dev)
+    for _ in range(warmup):
+        step.run(Z)
+    torch.cuda.synchronize(dev)
+    events.clear()
+    for _ in range(steps):
+        step.run(Z)
+    torch.cuda.synchronize(dev)
+    ph = {p: 0.0 for p in PHASES}
+    for (n0, e0), (n1, e1) in zip(events[:-1], events[1:]):
+        if n1 != "begin":
+            ph[n1] += e0.elapsed_time(e1)
+    ph = {p: v / steps for p, v in ph.items()}
+    nnz = step.graph.nnz
+    t_factor = ph["attn_fwd"] + ph["spmm_fwd"] + ph["bwd_gather"] + ph["bwd_edges"]
+    ab = alg_bytes(nnz, N, K, d, int(u.numel()))
+    fb = ab["attn_fwd"] + ab["spmm_fwd"] + ab["bwd_gather"] + ab["bwd_edges"]
+    out = {"N": int(N), "nnz": int(nnz), "K": K, "d": d, "P": int(u.numel()),
+           "value_edges_per_s": nnz / (t_factor * 1e-3), "pair_scores_per_s": int(u.numel()) / (ph["pair_fwd"] * 1e-3),
+           "ms": {k: round(ph[k], 4) for k in KERNEL_PHASES},
+           "factor_agg_fwd_bwd": {"alg_bytes": int(fb), "GB/s": round(fb / (t_factor * 1e-3) / 1e9, 1),
+                                  "frac": round(fb / (t_factor * 1e-3) / 1e9 / peak, 4)},
+           "working_set": "exceeds L2" if N * K * d * 4 > 2 * 126e6 else "fits L2 (launch / latency bound: not roofline evidence)",
+           "loss": float(step.loss.item())}
+    if note:
+        out["note"] = note
+    del step, Z
+    torch.cuda.empty_cache()
+    return out
+
+
+def other_configs(dev, peak):
+    """BASELINE.json configs[0..3] on one GPU: real graphs where the reference ships them (staged in
+    baseline/_ref or committed as a fixture), synthetic snap-patents-scale otherwise."""
+    import numpy as np
+    import torch
+    from disenlink_b200 import data as dl_data
+    out = {}
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+
+    def real(name, ei, N, shapes, note):
+        tr = dl_data.split_edges(ei.shape[1], seed=0)[0]
+        src, dst = ei[0][tr].to(dev), ei[1][tr].to(dev)
+        for (K, d, beta) in shapes:
+            try:
+                out[f"{name}_K{K}_d{d}"] = measure_config(name, src, dst, N, K, d, beta, dev, peak, steps=20, note=note)
+            except Exception as ex:                      # never lose the headline line to a side config
+                out[f"{name}_K{K}_d{d}"] = {"error": repr(ex)[:200]}
+    cora = os.path.join(ref_dir, "data", "cora", "raw")
+    if os.path.exists(cora):
+        _, ei, _ = dl_data.read_planetoid(cora, "cora")
+        real("c1_cora", ei, 2708, [(3, 32, 0.9), (10, 64, 0.6)], "real Cora graph, 85 % train columns; Z ~ N(0, d^-1/2)")
+    cham = os.path.join(ref_dir, "data_pre_false", "chameleon", "raw", "chameleon.npz")
+    if os.path.exists(cham):
+        x, ei, _ = dl_data.read_wikipedia_npz(cham)
+        real("c2_chameleon", ei, int(x.shape[0]), [(5, 32, 0.7)], "real chameleon graph (72 202 stored columns)")
+    sq = os.path.join(ref_dir, "data", "squirrel", "geom_gcn", "raw", "out1_graph_edges.txt")
+    if os.path.exists(sq):
+        e = torch.from_numpy(np.loadtxt(sq, skiprows=1, dtype=np.int64).T.copy())
+        real("c2_squirrel", e, int(e.max()) + 1, [(5, 64, 0.5)], "real squirrel graph (hyperparameters_setting:3)")
+    pm = os.path.join(ROOT, "tests", "golden", "pubmed_graph.npz")
+    if os.path.exists(pm):
+        gd = np.load(pm)
+        ei = torch.from_numpy(np.stack([gd["src"], gd["dst"]]).astype(np.int64))
+        real("c3_pubmed", ei, int(gd["N"]), [(8, 8, 0.6), (8, 64, 0.6)], "real Pubmed graph, K=8, both readings of d=64 (D=64, D=512)")
+    for key, K, d in (("c4_K8_d16", 8, 16), ("c4_K5_d32", 5, 32), ("c4_K5_d64", 5, 64)):
+        try:
+            wl = WORKLOADS["c4"]
+            src, dst = gen_edges(wl["N"], wl["E"], 0, dev)
+            out[key] = measure_config(key, src, dst, wl["N"], K, d, 0.5, dev, peak, steps=10, P=wl["P"],
+                                      note="snap-patents-scale synthetic power-law graph")
+            del src, dst
+        except Exception as ex:
+            out[key] = {"error": repr(ex)[:200]}
+    return out
 
 # ------------------------------------------------------------------------------------------------
 # native arm
@@ -378,6 +578,14 @@ def run_native(args):
         gbs = ab[kname] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         kernels[kname] = {"ms": round(ms, 4), "alg_bytes": int(ab[kname]), "GB/s": round(gbs, 1),
                           "frac": round(gbs / peak, 4)}
+    # SURVEY's P(16D+12) counts four full rows per pair; the pairs are sorted by u and come in groups of
+    # 1 + M_NEG sharing u, so z_u / h_u are read once per group: the honest floor is P(8D(1 + 1/(1+m)) + 12)
+    pf_ms = phase_ms["pair_fwd"]
+    pf_sorted = (step.p_hi - step.p_lo) * (8 * D * (1 + 1.0 / (1 + M_NEG)) + 12)
+    kernels["pair_fwd"]["alg_bytes_u_sorted"] = int(pf_sorted)
+    kernels["pair_fwd"]["frac_u_sorted"] = round(pf_sorted / (pf_ms * 1e-3) / 1e9 / peak, 4) if pf_ms > 0 else 0.0
+    kernels["pair_fwd"]["note"] = ("frac uses SURVEY 8(d)'s P(16D+12) (no credit for the u-sorted 1+m groups) and reads "
+                                   "above 1; frac_u_sorted uses P(8D(1+1/(1+m))+12), the bytes a read-only stream must move")
     dom = max(KERNEL_PHASES, key=lambda k: phase_ms[k])
     fwd_bwd_bytes = ab["attn_fwd"] + ab["spmm_fwd"] + ab["bwd_gather"] + ab["bwd_edges"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GB/s"], "peak": peak, "unit": "GB/s",
@@ -516,7 +724,15 @@ def run_native(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    configs = None
+    if world == 1 and not args.no_configs:
+        # drop the headline workload's buffers (rebinding also clears the cells the e2e closures hold)
+        g_full = batch = Zbufs = Z_host = prob_host = last = step = Z = prob_d = None  # noqa: F841
+        torch.cuda.empty_cache()
+        configs = other_configs(dev, peak)
     cb = cpu_baseline(K, d, beta, T) if (world == 1 and not args.no_cpu) else None
+    if cb is not None:
+        cb["dense_reference"] = dense_reference_leg(dev)
 
     line = {
         "metric": "factor-agg edges/s (fwd+bwd)", "value": value, "unit": "edges/s", "n_gpus": world,
@@ -543,6 +759,8 @@ def run_native(args):
         line["next_rows"] = extras
     if cb is not None:
         line["cpu_baseline"] = cb
+    if configs is not None:
+        line["other_configs"] = configs
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -557,6 +775,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("DL_BENCH_WORKLOAD", "c5"), choices=list(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the side measurements of BASELINE configs[0..3]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -191,23 +191,18 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
   DlChunkStream cs;
   cs.init(g.nnz, (long long)gridDim.x * GS_WARPS);
 
-  // per-chunk metadata.  Loads are unconditional from a clamped index and the three Meta objects are used
-  // in rotating ROLES by a 3x unrolled loop (no register moves): a select or a MOV on a just-loaded
-  // register makes the warp wait for the load on the spot (ncu: those were the top stall sites).
-  struct Meta { int row, col, ks; float wv, sj; bool valid; };
+  struct Meta { int row, col, ks; float wv; };
   auto load_meta = [&](long long cc, Meta& m) {
-    const long long e = cc * DL_CH + lane;
-    m.valid = cc >= 0 && e < g.nnz;
-    const long long ec = m.valid ? e : 0;
-    m.row = __ldg(g.erow + ec);
-    m.ks = __ldg(kstar + ec);
-    m.wv = __ldg(w + ec);
-    m.col = (MODE != 2) ? __ldg(g.col + ec) : 0;
-    m.sj = 1.0f;
-  };
-  // applied when the chunk becomes "next" (its loads were issued one iteration earlier)
-  auto settle_meta = [&](Meta& m) {
-    if (!m.valid) { m.row = -1; m.ks = 255; m.wv = 0.0f; m.col = 0; }
+    m.row = -1; m.col = 0; m.ks = 255; m.wv = 0.0f;
+    if (cc >= 0) {
+      const long long e = cc * DL_CH + lane;
+      if (e < g.nnz) {
+        m.row = __ldg(g.erow + e);
+        m.ks = __ldg(kstar + e);
+        m.wv = __ldg(w + e);
+        if (MODE != 2) m.col = __ldg(g.col + e);
+      }
+    }
   };
   auto issue_slices = [&](unsigned char* buf, const Meta& m) {
     if (MODE == 2) return;
@@ -335,24 +330,22 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
   };
 
   long long c = cs.first(gw);
-  Meta m0, m1, m2;
-  load_meta(c, m0);
-  settle_meta(m0);
+  Meta mA, mB, mC;
+  load_meta(c, mA);
   long long cn = cs.next(c);
-  load_meta(cn, m1);
+  load_meta(cn, mB);
+  float sjA = 1.0f, sjB = 1.0f;
   // s == nullptr in MODE 0: SRC holds slices already divided by s (factor_fwd.cu k_scale_rows)
-  if (MODE == 0 && s != nullptr && m0.ks != 255) m0.sj = gs_ldg_s(s + (long long)m0.col * K + m0.ks);
+  if (MODE == 0 && s != nullptr && mA.ks != 255) sjA = gs_ldg_s(s + (long long)mA.col * K + mA.ks);
   int buf = 0;
-  issue_slices(tile, m0);
+  issue_slices(tile, mA);
   dl_cp_async_commit();
 
-  // one iteration: mA = current chunk, mB = next (loads issued an iteration ago), mC = the one after
-  auto step = [&](Meta& mA, Meta& mB, Meta& mC) {
+  while (c >= 0) {
     // pipeline: metadata two chunks ahead, s gather + slices one chunk ahead
     const long long cnn = cs.next(cn);
     load_meta(cnn, mC);
-    settle_meta(mB);
-    if (MODE == 0 && s != nullptr && mB.ks != 255) mB.sj = gs_ldg_s(s + (long long)mB.col * K + mB.ks);
+    if (MODE == 0 && s != nullptr && mB.ks != 255) sjB = gs_ldg_s(s + (long long)mB.col * K + mB.ks);
     issue_slices(tile + (buf ^ 1) * TILE_B, mB);
     dl_cp_async_commit();
     dl_cp_async_wait<1>();
@@ -371,8 +364,8 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
 
     // MODE 0 has no r output: the pointer carries the optional per-entry copy of s[col, kstar]
     // (sj_out of dl_factor_spmm_fwd) that lets backward pass 2 skip this gather
-    if (MODE == 0 && r != nullptr && s != nullptr && mA.row >= 0) r[c * DL_CH + lane] = mA.sj;
-    const float coefA = (MODE == 0 && s != nullptr) ? __fdiv_rn(mA.wv, mA.sj) : mA.wv;
+    if (MODE == 0 && r != nullptr && s != nullptr && mA.row >= 0) r[c * DL_CH + lane] = sjA;
+    const float coefA = (MODE == 0) ? __fdiv_rn(mA.wv, sjA) : mA.wv;
     const unsigned vmask = __ballot_sync(DL_FULL, mA.row >= 0);
     const int cnt = __popc(vmask);
     const unsigned char* sl = tile + buf * TILE_B;
@@ -399,7 +392,7 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
     } else {
       // Every lane group walks only the entries routed to ITS factor: mine[p] has bit i set when
       // entry i of the chunk belongs to factor p*FPP + slot.  The walk is divergent between lane
-      // groups (no shuffles across groups: coefficients and slices come from shared memory) and costs
+      // groups (no shuffles inside: coefficients and slices come from shared memory) and costs
       // max-over-factors entries per run instead of all of them; each accumulator still receives
       // its entries in CSR order, so the sums are bit-identical to an entry-by-entry walk.
       cfbuf[lane] = coefA;
@@ -447,13 +440,8 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
     if (MODE == 1 && want_x && mA.row >= 0) xout[c * DL_CH + lane] = xbuf[lane];
     buf ^= 1;
     c = cn; cn = cnn;
-  };
-  while (c >= 0) {
-    step(m0, m1, m2);
-    if (c < 0) break;
-    step(m1, m2, m0);
-    if (c < 0) break;
-    step(m2, m0, m1);
+    mA = mB; mB = mC;
+    sjA = sjB;
   }
   if (cur_range >= 0) flush(true);
   dl_cp_async_wait<0>();

@@ -63,15 +63,23 @@ def read_planetoid(raw_dir: str, name: str, sparse_x: bool = False):
     return xt, edge_index, torch.from_numpy(y.astype(np.int64))
 
 
-def read_wikipedia_npz(path: str):
-    """-> (x [N,F] float32, edge_index [2,E] int64 as stored (directed columns), y [N] int64).
-    chameleon: N=2277, F=128, E=72202 directed columns before PyG's coalesce."""
+def read_wikipedia_npz(path: str, coalesce: bool = False):
+    """-> (x [N,F] float32, edge_index [2,E] int64, y [N] int64).
+    Default = the reference's own reader (dataset.py:119-124): `edges.t()` exactly as stored -- directed
+    columns, duplicates KEPT, no to_undirected (commented out at :123).  chameleon: N=2277, F=128,
+    E=72202 columns of which 9410 are duplicates and 100 self loops.  The duplicates matter downstream:
+    they change the 85/10/5 split sizes (main_disentangled.py:134) and which positives the `== 1`
+    loss mask drops (:175-178,195).  coalesce=True gives the sorted de-duplicated columns (62792) that
+    PyG's coalescing loaders would."""
     d = np.load(path, allow_pickle=True)
     x = torch.from_numpy(np.asarray(d["features"], dtype=np.float32))
     e = np.asarray(d["edges"], dtype=np.int64)
     n = x.shape[0]
-    key = np.unique(e[:, 0] * n + e[:, 1])               # PyG coalesces: sorted, duplicates removed
-    edge_index = torch.from_numpy(np.stack([key // n, key % n]))
+    if coalesce:
+        key = np.unique(e[:, 0] * n + e[:, 1])
+        edge_index = torch.from_numpy(np.stack([key // n, key % n]))
+    else:
+        edge_index = torch.from_numpy(np.ascontiguousarray(e.T))
     y = torch.from_numpy(np.asarray(d["label"] if "label" in d.files else d["target"]).astype(np.int64))
     return x, edge_index, y
 

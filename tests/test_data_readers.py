@@ -31,7 +31,15 @@ def test_planetoid_cora_matches_pyg_canonical_numbers():
 def test_wikipedia_npz_chameleon():
     x, ei, y = data.read_wikipedia_npz(CHAM)
     assert tuple(x.shape) == (2277, 128) and tuple(y.shape) == (2277,)
-    assert ei.shape[1] == 62792                                              # 72202 stored columns, coalesced
+    # the reference's reader keeps the stored columns as they are (dataset.py:119-124): 72202 columns,
+    # 9410 of them duplicates, 100 self loops, not symmetrised
+    assert ei.shape[1] == 72202
+    raw = np.load(CHAM, allow_pickle=True)["edges"]
+    assert np.array_equal(ei.numpy(), raw.T)
+    key = ei[0] * 2277 + ei[1]
+    assert key.numel() - torch.unique(key).numel() == 9410 and int((ei[0] == ei[1]).sum()) == 100
+    _, eic, _ = data.read_wikipedia_npz(CHAM, coalesce=True)
+    assert eic.shape[1] == 62792 and torch.equal(eic[0] * 2277 + eic[1], torch.unique(key))
     xs = data.row_standardize(x)
     assert float(xs.mean(dim=1).abs().max()) < 1e-5
     assert float((xs.std(dim=1) - 1).abs().max()) < 1e-4
