@@ -91,14 +91,23 @@ def gen_pairs(rowptr, col, N, P, seed, device):
     return u[order], v[order], lab[order], wts[order]
 
 
-def gen_Z(n_rows, K, d, seed, device):
+Z_CHUNK = 1 << 22
+
+
+def gen_Z(n_rows, K, d, seed, device, row0=0, out=None):
+    """Rows [row0, row0 + n_rows) of the synthetic factor embeddings.  Every block of Z_CHUNK rows has its
+    own generator seed, so a rank of a node-partitioned run draws exactly the rows it owns and they are
+    the rows a single-GPU run draws."""
     import torch
-    g = torch.Generator(device=device).manual_seed(seed + 2)
-    Z = torch.empty(n_rows, K, d, dtype=torch.float32, device=device)
-    chunk = 1 << 22
-    for a in range(0, n_rows, chunk):
-        b = min(n_rows, a + chunk)
-        Z[a:b] = torch.randn(b - a, K, d, generator=g, device=device) * (d ** -0.25)  # q = O(1)
+    Z = out if out is not None else torch.empty(n_rows, K, d, dtype=torch.float32, device=device)
+    scale = d ** -0.25                                                      # q = O(1)
+    c0, c1 = row0 // Z_CHUNK, (row0 + n_rows + Z_CHUNK - 1) // Z_CHUNK
+    for c in range(c0, c1):
+        g = torch.Generator(device=device).manual_seed((seed + 2) * 1_000_003 + c)
+        blk = torch.randn(Z_CHUNK, K, d, generator=g, device=device)
+        a, b = max(row0, c * Z_CHUNK), min(row0 + n_rows, (c + 1) * Z_CHUNK)
+        Z[a - row0:b - row0] = blk[a - c * Z_CHUNK:b - c * Z_CHUNK] * scale
+        del blk
     return Z
 
 
@@ -351,13 +360,13 @@ def measure_config(name, src, dst, N, K, d, beta, dev, peak, steps=10, warmup=3,
         ev.record(torch.cuda.current_stream(dev))
         events.append((nm, ev))
     step = PartitionedLinkStep(src, dst, N, u, v, lab, wts, K, d, beta, 1.0, world=1, rank=0, device=dev, mark=mark)
-    Z = gen_Z(step.part.n_pad, K, d, 0, dev)
+    gen_Z(N, K, d, 0, dev, out=step.Z_own)
     for _ in range(warmup):
-        step.run(Z)
+        step.run()
     torch.cuda.synchronize(dev)
     events.clear()
     for _ in range(steps):
-        step.run(Z)
+        step.run()
     torch.cuda.synchronize(dev)
     ph = {p: 0.0 for p in PHASES}
     for (n0, e0), (n1, e1) in zip(events[:-1], events[1:]):
@@ -377,7 +386,7 @@ def measure_config(name, src, dst, N, K, d, beta, dev, peak, steps=10, warmup=3,
            "loss": float(step.loss.item())}
     if note:
         out["note"] = note
-    del step, Z
+    del step
     torch.cuda.empty_cache()
     return out
 
@@ -427,6 +436,87 @@ def other_configs(dev, peak):
             out[key] = {"error": repr(ex)[:200]}
     return out
 
+
+# ------------------------------------------------------------------------------------------------
+# N > 1: the partitioned step against a single-GPU step on the same inputs (every rank checks its rows)
+# ------------------------------------------------------------------------------------------------
+def multi_gpu_parity(world, rank, dev, workload="mid"):
+    import torch
+    import torch.distributed as dist
+    from disenlink_b200.partition import PartitionedLinkStep
+    wl = WORKLOADS[workload]
+    N, E, K, d, P, beta, T = (wl[k] for k in ("N", "E", "K", "d", "P", "beta", "T"))
+    src, dst = gen_edges(N, E, 0, dev)
+    u, v, lab, wts = gen_pairs_from_edges(src, dst, N, E, P, dev)
+    part_step = PartitionedLinkStep(src, dst, N, u, v, lab, wts, K, d, beta, T, world=world, rank=rank, device=dev)
+    lo, hi = part_step.part.lo, part_step.part.hi
+    gen_Z(hi - lo, K, d, 0, dev, row0=lo, out=part_step.Z_own)
+    for it in range(2):                       # two steps, Z changed in between (exchange ordering)
+        if it == 1:
+            part_step.Z_own.mul_(1.25)
+        part_step.run()
+    single = PartitionedLinkStep(src, dst, N, u, v, lab, wts, K, d, beta, T, world=1, rank=0, device=dev)
+    gen_Z(N, K, d, 0, dev, out=single.Z_own)
+    single.Z_own.mul_(1.25)
+    single.run()
+    torch.cuda.synchronize(dev)
+    e0, e1 = int(single.graph.rowptr[lo]), int(single.graph.rowptr[hi])
+    nl = part_step.graph.nnz
+    halo = part_step.plan.halo
+    col_g = torch.where(part_step.graph.col.long() < part_step.n_own, part_step.graph.col.long() + lo,
+                        halo[(part_step.graph.col.long() - part_step.n_own).clamp_(min=0)]) if nl else None
+    ok_int = (e1 - e0 == nl) and bool(torch.equal(col_g.int(), single.graph.col[e0:e1]))
+    ok_int = ok_int and bool(torch.equal(part_step.kstar[:nl], single.kstar[e0:e1]))
+    ok_int = ok_int and bool(torch.equal(part_step.w[:nl], single.w[e0:e1]))
+    pos = torch.arange(e0, e1, device=dev, dtype=torch.int64) % 1_000_003 + 1
+    khash = (part_step.kstar[:nl].long() * pos).sum()
+    khash_single = (single.kstar[:single.graph.nnz].long() *
+                    (torch.arange(single.graph.nnz, device=dev, dtype=torch.int64) % 1_000_003 + 1)).sum()
+
+    def rel(a, b):
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    n = part_step.n_own
+    errs = {"s": rel(part_step.s[:n], single.s[lo:hi]), "H": rel(part_step.H[:n], single.H[lo:hi]),
+            "r": rel(part_step.r[:n], single.r[lo:hi]), "dZ": rel(part_step.dZ, single.dZ[lo:hi]),
+            "dH": rel(part_step.dH[:n], single.dH[lo:hi]),
+            "prob": float((part_step.prob[:P] - single.prob[:P]).abs().max())}
+    vol = part_step.exchange_volume()
+    t = torch.tensor([float(ok_int)] + [-e for e in errs.values()], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    hs = khash.clone()
+    dist.all_reduce(hs)
+    out = {"workload": wl["name"], "steps": 2,
+           "integers_and_routing_bitwise_equal": bool(t[0].item() == 1.0),
+           "kstar_hash": int(hs.item()), "kstar_hash_single_gpu": int(khash_single.item()),
+           "max_rel_err_vs_single_gpu": {k: -float(x) for k, x in zip(errs.keys(), t[1:].tolist())},
+           "loss": float(part_step.loss.item()), "loss_single_gpu": float(single.loss.item()),
+           "rank0_rows": vol, "exchange": "NVLink peer push" if part_step.pushed else "torch.distributed p2p"}
+    out["ok"] = (out["integers_and_routing_bitwise_equal"] and out["kstar_hash"] == out["kstar_hash_single_gpu"]
+                 and all(e < 1e-5 for e in out["max_rel_err_vs_single_gpu"].values()))
+    part_step.close()
+    del part_step, single
+    torch.cuda.empty_cache()
+    return out
+
+
+def gen_pairs_from_edges(src, dst, N, E, P, dev):
+    """every rank draws the same pairs: positives are directed edge columns (each is an entry of adj_sym),
+    M_NEG uniform negatives share u with their positive (main_disentangled.py:159-163); sorted by u so the
+    (1 + M_NEG) pairs of one u are adjacent"""
+    import torch
+    gp = torch.Generator(device=dev).manual_seed(1)
+    P_pos = max(P // (1 + M_NEG), 1)
+    e = torch.randint(0, E, (P_pos,), generator=gp, device=dev)
+    pu, pv = src[e], dst[e]
+    nu = pu.repeat(M_NEG)
+    nv = torch.randint(0, N, (P_pos * M_NEG,), generator=gp, device=dev)
+    u, v = torch.cat([pu, nu]), torch.cat([pv, nv])
+    lab = torch.cat([torch.ones(P_pos, device=dev), torch.zeros(P_pos * M_NEG, device=dev)])
+    wts = torch.cat([torch.full((P_pos,), 1.0 / P_pos, device=dev),
+                     torch.full((P_pos * M_NEG,), 1.0 / (M_NEG * P_pos * M_NEG), device=dev)])
+    order = torch.sort(u, stable=True).indices
+    return u[order], v[order], lab[order], wts[order]
+
 # ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
@@ -454,32 +544,19 @@ def run_native(args):
     wl = dict(WORKLOADS[args.workload])
     N, E, K, d, P, beta, T = (wl[k] for k in ("N", "E", "K", "d", "P", "beta", "T"))
     D = K * d
-    # memory guard: ~4 [N,K,d] fp32 buffers + graph + pairs must fit (per rank the node arrays are full size)
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = multi_gpu_parity(world, rank, dev)
+    # memory guard (one GPU; a partitioned run holds own + halo rows only): ~4 [N,K,d] fp32 buffers + graph + pairs
     free_b, total_b = torch.cuda.mem_get_info(dev)
-    need = int(4.4 * N * D * 4) + 2 * E * 10 // world + 56 * E // world + 16 * E + P * 50 + (4 << 30)
-    need = max(int(4.4 * N * D * 4) + 2 * E * 10 // world + P * 50, 16 * E + 56 * E // world) + (4 << 30)
-    if need > free_b:
+    need = max(int(4.4 * N * D * 4) + 2 * E * 10 + P * 50, 16 * E + 56 * E) + (4 << 30)
+    if world == 1 and need > free_b:
         raise SystemExit(f"workload {args.workload} needs ~{need / 2**30:.0f} GiB, {free_b / 2**30:.0f} GiB free")
 
     t_setup = time.perf_counter()
     src, dst = gen_edges(N, E, 0, dev)
     from disenlink_b200.graph import Graph
-    # every rank draws the same pairs: positives are directed edge columns (each is an entry of
-    # adj_sym), M_NEG uniform negatives share u with their positive (main_disentangled.py:159-163);
-    # sorted by u so the (1 + M_NEG) pairs of one u are adjacent
-    gp = torch.Generator(device=dev).manual_seed(1)
-    P_pos = max(P // (1 + M_NEG), 1)
-    e = torch.randint(0, E, (P_pos,), generator=gp, device=dev)
-    pu, pv = src[e], dst[e]
-    nu = pu.repeat(M_NEG)
-    nv = torch.randint(0, N, (P_pos * M_NEG,), generator=gp, device=dev)
-    u, v = torch.cat([pu, nu]), torch.cat([pv, nv])
-    lab = torch.cat([torch.ones(P_pos, device=dev), torch.zeros(P_pos * M_NEG, device=dev)])
-    wts = torch.cat([torch.full((P_pos,), 1.0 / P_pos, device=dev),
-                     torch.full((P_pos * M_NEG,), 1.0 / (M_NEG * P_pos * M_NEG), device=dev)])
-    order = torch.sort(u, stable=True).indices
-    u, v, lab, wts = u[order], v[order], lab[order], wts[order]
-    del e, pu, pv, nu, nv, order
+    u, v, lab, wts = gen_pairs_from_edges(src, dst, N, E, P, dev)
     P = int(u.numel())
 
     events = []
@@ -500,8 +577,9 @@ def run_native(args):
         t = torch.tensor([nnz_local], dtype=torch.int64, device=dev)
         dist.all_reduce(t)
         nnz_global = int(t.item())
-    Z = gen_Z(part.n_pad, K, d, 0, dev)   # every rank generates the same full Z; only own rows are "its"
-    pushed = step.register_input(Z)          # all-gathers as NVLink pushes when the ranks can map each other
+    gen_Z(part.n_local, K, d, 0, dev, row0=part.lo, out=step.Z_own)   # every rank draws the rows it owns
+    pushed = step.pushed                     # exchanges as NVLink pushes when the ranks can map each other
+    volume = step.exchange_volume()
     torch.cuda.synchronize(dev)
     t_setup = time.perf_counter() - t_setup
 
@@ -512,7 +590,7 @@ def run_native(args):
 
     # ---- device-timed loop ----
     for _ in range(args.warmup):
-        step.run(Z)
+        step.run()
     barrier()
     events.clear()
     launches0 = _lib.launches
@@ -523,7 +601,7 @@ def run_native(args):
     torch.cuda.profiler.start()      # ncu --profile-from-start off captures exactly the timed steps
     ev_a.record(torch.cuda.current_stream(dev))
     for _ in range(args.steps):
-        step.run(Z)
+        step.run()
     ev_b.record(torch.cuda.current_stream(dev))
     torch.cuda.profiler.stop()
     barrier()
@@ -544,15 +622,11 @@ def run_native(args):
         phase_ms = {p: float(x) for p, x in zip(PHASES, tt[1:].tolist())}
     ms_per_step = total_ms / args.steps
     t_factor = phase_ms["attn_fwd"] + phase_ms["spmm_fwd"] + phase_ms["bwd_gather"] + phase_ms["bwd_edges"]
-    t_comm_factor = phase_ms["ag_Z"] + phase_ms["ag_s"] + phase_ms["ag_H"] + phase_ms["ag_dH"] + phase_ms["ag_r"]
-    # With the exchange of dH fused into the decoder backward its cost sits inside the pair_bwd phase:
-    # count that whole phase (conservative: it includes the decoder's own compute) so that the metric
-    # never hides an exchange the factor path needs.
-    fused_exchange = world > 1 and pushed and not os.environ.get("DL_NO_FUSED_PUSH")
-    if fused_exchange:
-        t_comm_factor += phase_ms["pair_bwd"]
+    # the same definition at every N: the four factor kernels plus the exchanges THEY need (Z, s, the routed
+    # dH slices, r; all zero on one GPU).  The H and prob exchanges serve the pair scoring and count there.
+    t_comm_factor = phase_ms["ag_Z"] + phase_ms["ag_s"] + phase_ms["ag_dH"] + phase_ms["ag_r"]
     value = nnz_global / ((t_factor + t_comm_factor) * 1e-3)
-    pair_rate = P / ((phase_ms["pair_fwd"] + phase_ms["ag_prob"]) * 1e-3)
+    pair_rate = P / ((phase_ms["pair_fwd"] + phase_ms["ag_H"] + phase_ms["ag_prob"]) * 1e-3)
 
     # ---- roofline of the dominant kernel (per-rank bytes / per-rank time) ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -565,13 +639,14 @@ def run_native(args):
     # node-major decoder backward: per incidence the other endpoint's Z and H rows + 3 ids/floats,
     # per node 2 rows in and 2 rows out (less than SURVEY's scatter-form P*(32D+16): see DESIGN.md)
     ab["pair_bwd"] = int(step.inc.nnz) * (8 * D + 12) + part.n_local * 16 * D
-    # kernels of libdisenlink_b200.so per step (streaming path): attention = routing with fused row sums +
-    # chain + empty rows (3); aggregation = gather + chain + empty rows (3); pair scoring fwd (1);
-    # decoder backward = stream + chain + empty nodes (3); backward pass 1 (3); backward pass 2 =
-    # stream + chain (2); weighted BCE forward+backward (2)
-    launches_per_step = 17 + (1 if step.prescale else 0)     # + the Z/s streaming pass on one GPU
-    if world > 1 and pushed:                                  # + dl_push_slice for Z, prob (and s, H, dH, r unless fused)
-        launches_per_step += 6 if os.environ.get("DL_NO_FUSED_PUSH") else 2
+    # kernels of libdisenlink_b200.so per step (streaming path): attention = routing + row sums + chain +
+    # empty rows (3; one GPU, symmetric: upper-triangle routing + expand + chain + empty rows = 4); aggregation =
+    # gather + chain + empty rows (3; + the Z/s streaming pass on one GPU); pair scoring fwd (1); weighted BCE (2);
+    # decoder backward = stream + chain + empty nodes (3); backward pass 1 (3); backward pass 2 = (s,r) pack +
+    # stream + chain (3)
+    launches_per_step = 18 + (2 if world == 1 else 0)
+    if world > 1 and pushed:                                  # + need-masks, pushes of Z, s, H, dH, r, prob
+        launches_per_step += 7
     kernels = {}
     for kname in KERNEL_PHASES:
         ms = phase_ms[kname]
@@ -606,14 +681,13 @@ def run_native(args):
     # ---- end to end through the public autograd API, host buffers ----
     e2e = None
     if world == 1 and not args.no_e2e:
+        Z_host = torch.empty(N, K, d, dtype=torch.float32).pin_memory()
+        Z_host.copy_(step.Z_own)
         del step
         torch.cuda.empty_cache()
         g_full = Graph.from_edges(*gen_edges(N, E, 0, dev), N)
         batch = ops.PairBatch(u, v, N)
         batch.incidence()
-        Z_host = torch.empty(N, K, d, dtype=torch.float32).pin_memory()
-        Z_host.copy_(Z[:N])
-        del Z
         torch.cuda.empty_cache()
         prob_host = torch.empty(P, dtype=torch.float32).pin_memory()
         # Input staging: Z comes from pinned host memory every step.  Two device buffers and a copy
@@ -694,6 +768,57 @@ def run_native(args):
                                  "of step t" if nb > 1 else "single buffer: upload serial with the kernels"),
                "loss": e2e_loss}
 
+    # ---- N > 1: end to end through the partitioned step's public API: every rank uploads the embeddings of
+    # the nodes it owns from pinned host memory (a staging buffer on a copy stream takes step t+1's upload
+    # while step t runs), runs the step and reads back the loss and its share of the scores ----
+    if world > 1 and not args.no_e2e:
+        n_own = step.n_own
+        Zh = torch.empty(n_own, K, d, dtype=torch.float32).pin_memory()
+        Zh.copy_(step.Z_own)
+        lo_p = rank * step.p_per
+        n_p = step.p_hi - step.p_lo
+        prob_host = torch.empty(max(n_p, 1), dtype=torch.float32).pin_memory()
+        stage = torch.empty(n_own, K, d, dtype=torch.float32, device=dev)
+        copy_stream = torch.cuda.Stream(dev)
+        ready, free = torch.cuda.Event(), torch.cuda.Event()
+        free.record(torch.cuda.current_stream(dev))
+
+        def upload():
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free)
+                stage.copy_(Zh, non_blocking=True)
+                ready.record(copy_stream)
+
+        def e2e_multi(n_steps):
+            val = 0.0
+            for _ in range(n_steps):
+                cur = torch.cuda.current_stream(dev)
+                cur.wait_event(ready)
+                step.Z_own.copy_(stage)
+                free.record(cur)
+                upload()                                        # next step's input, overlapped with this step
+                step.run()
+                prob_host.copy_(step.prob[lo_p:lo_p + n_p] if n_p else step.prob[:1], non_blocking=True)
+                val = step.loss.item()
+            torch.cuda.synchronize(dev)
+            return val
+        upload()
+        e2e_multi(max(args.warmup, 1))
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loss = e2e_multi(args.steps)
+        barrier()
+        tt = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+        e2e = {"value": nnz_global / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": round(e2e_ms, 3),
+               "h2d_bytes_per_step": int(N * D * 4), "d2h_bytes_per_step": int(P * 4 + 4 * world),
+               "api": "PartitionedLinkStep.run(Z_own) on every rank; Z_own from pinned host memory (N*D*4 bytes over all "
+                      "ranks), loss + the rank's share of the P scores read back; wall clock between barriers, max over ranks",
+               "input_staging": "staging buffer on a copy stream: the upload of step t+1 overlaps the kernels of step t",
+               "loss": e2e_loss}
+        step.close()
+
     # ---- the evaluation-side kernels of SURVEY 8(f) on the same data: AUC of the P scores, one
     # round of structured negative sampling against the resident CSR (device-timed, outside the step) ----
     extras = None
@@ -741,12 +866,13 @@ def run_native(args):
         "data": "synthetic",
         "config": {"workload": wl["name"], "N": N, "E_directed": E, "nnz": nnz_global, "K": K, "d": d, "P": P,
                    "beta": beta, "T": T, "parallelism": "1 GPU" if world == 1 else (
-                       f"node-partitioned x{world}, exchanges over NVLink peer memory: s, H, dH and r stored into the peers by the kernels that produce them, Z and the scores by dl_push_slice" if pushed
-                       else f"node-partitioned x{world}, NCCL all-gather"),
+                       f"node-partitioned x{world} (nnz-balanced ranges, rank-local storage = own + halo rows); owners push "
+                       "what the reader reads over NVLink peer memory: halo rows of Z, s, r, H rows of the pair endpoints, "
+                       "routed slices of dH" if pushed
+                       else f"node-partitioned x{world}, torch.distributed point-to-point halo exchange"),
                    "l2": f"inputs exceed L2: Z alone is {N * D * 4 / 2**30:.1f} GiB vs 126 MB L2 (no flush needed)",
-                   "value_definition": "nnz / (attention + aggregation + both backward passes"
-                                       + ((" + their all-gathers" + (" + the decoder backward that carries the dH exchange)"
-                                                                    if fused_exchange else ")")) if world > 1 else ")")},
+                   "value_definition": "nnz / (attention + aggregation + both backward passes + the halo exchanges they "
+                                       "need: Z, s, routed dH slices, r -- zero on one GPU); the same at every N"},
         "pair_scores_per_s": pair_rate,
         "phases_ms": {k: round(v, 4) for k, v in phase_ms.items()},
         "kernels": kernels, "roofline": roofline, "clocks": clocks,
@@ -755,6 +881,10 @@ def run_native(args):
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if parity is not None:
+        line["parity"] = parity
+    if world > 1:
+        line["partition"] = {"bounds": part.bounds, "rank0": volume}
     if extras is not None:
         line["next_rows"] = extras
     if cb is not None:
@@ -775,6 +905,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("DL_BENCH_WORKLOAD", "c5"), choices=list(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the comparison with a single-GPU step")
     ap.add_argument("--no-configs", action="store_true", help="skip the side measurements of BASELINE configs[0..3]")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -54,6 +54,11 @@ class DlGraph(_c.Structure):
                 ("erow", _vp), ("row_base", _i64), ("flags", _c.c_uint32)]
 
 
+class DlPushDesc(_c.Structure):
+    """Mirror of ``struct dl_push_desc``."""
+    _fields_ = [("dst", _vp), ("src_idx", _vp), ("dst_idx", _vp), ("mask", _vp), ("n", _i64)]
+
+
 _GP = _c.POINTER(DlGraph)
 
 # name -> (restype, argtypes); every symbol declared in include/disenlink_b200.h
@@ -92,6 +97,8 @@ SIGNATURES = {
     "dl_roc_auc_workspace_bytes": (_i64, [_i64]),
     "dl_roc_auc": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "dl_push_slice": (_int, [_vp, _vp, _int, _i64, _vp]),
+    "dl_push_rows": (_int, [_vp, _i64, _int, _c.POINTER(DlPushDesc), _int, _vp]),
+    "dl_need_masks": (_int, [_GP, _vp, _vp, _int, _vp, _vp]),
     "dl_factor_spmm_fwd_push": (_int, [_GP, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp, _vp, _int, _vp]),
     "dl_edge_attn_fwd_push": (_int, [_GP, _vp, _int, _int, _f, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "dl_factor_bwd_gather_push": (_int, [_GP, _vp, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),

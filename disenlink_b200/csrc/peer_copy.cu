@@ -67,6 +67,99 @@ extern "C" int dl_push_slice(const void* src, void* const* peer_dst, int n_peers
   return DL_OK;
 }
 
+// ---- halo exchange: the owner pushes exactly the rows (or routed slices) a peer reads -----------------
+namespace {
+
+struct PushTable {
+  dl_push_desc d[DL_MAX_PEERS];
+};
+
+// one thread per 16-byte vector of a pushed row; blockIdx.y = peer.  vpf > 0: the row is K factor slices of
+// vpf vectors each and only the slices whose bit is set in mask[source row] are sent.
+__global__ void __launch_bounds__(256)
+k_push_rows(const uint4* __restrict__ src, int vpr, int vpf, PushTable tab) {
+  const dl_push_desc d = tab.d[blockIdx.y];
+  uint4* __restrict__ dst = reinterpret_cast<uint4*>(d.dst);
+  const long long total = (long long)d.n * vpr;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long t = i / vpr;
+    const int c = (int)(i - t * vpr);
+    const long long sr = d.src_idx ? (long long)__ldg(d.src_idx + t) : t;
+    if (vpf > 0 && d.mask && !((__ldg(d.mask + sr) >> (c / vpf)) & 1u)) continue;
+    const long long dr = d.dst_idx ? (long long)__ldg(d.dst_idx + t) : t;
+    dst[dr * vpr + c] = __ldg(src + sr * vpr + c);
+  }
+}
+
+// masks[part][row] |= 1 << kstar[e] for every entry e = (row, col) whose column belongs to part's halo block
+__global__ void __launch_bounds__(256)
+k_need_masks(DlGraphDev g, const unsigned char* __restrict__ kstar, const int* __restrict__ halo_off, int n_parts,
+             unsigned* __restrict__ masks) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long nnz32 = (g.nnz + 31) / 32 * 32;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz32; e += stride) {
+    int key = -1;
+    unsigned bit = 0;
+    if (e < g.nnz) {
+      const int c = __ldg(g.col + e);
+      if (c >= g.N) {                                        // a halo column: find its owner's block
+        int part = 0;
+        while (part + 1 < n_parts && c >= __ldg(halo_off + part + 1)) ++part;
+        key = __ldg(g.erow + e) * 16 + part;                 // n_parts <= 16
+        bit = 1u << __ldg(kstar + e);
+      }
+    }
+    // consecutive entries of a row are column-sorted, i.e. grouped by owner: OR inside the warp first
+    const unsigned same = __match_any_sync(DL_FULL, key);
+    const unsigned bits = __reduce_or_sync(same, bit);
+    if (key >= 0 && (__ffs(same) - 1) == (int)(threadIdx.x & 31))
+      atomicOr(masks + (long long)(key & 15) * g.N + (key >> 4), bits);     // integer: order independent
+  }
+}
+
+}  // namespace
+
+extern "C" int dl_push_rows(const void* src, int64_t row_bytes, int vec_per_factor, const dl_push_desc* descs_host,
+                            int n_peers, dl_stream_t stream) {
+  if (n_peers < 0 || n_peers > DL_MAX_PEERS || row_bytes <= 0 || row_bytes % 16 || vec_per_factor < 0) return DL_EINVAL;
+  if (n_peers == 0) return DL_OK;
+  if (!src || !descs_host || ((uintptr_t)src & 15) != 0) return DL_EINVAL;
+  PushTable tab;
+  long long most = 0;
+  for (int q = 0; q < n_peers; ++q) {
+    tab.d[q] = descs_host[q];
+    if (tab.d[q].n < 0 || (tab.d[q].n > 0 && (!tab.d[q].dst || ((uintptr_t)tab.d[q].dst & 15) != 0))) return DL_EINVAL;
+    if (tab.d[q].n > most) most = tab.d[q].n;
+  }
+  if (most == 0) return DL_OK;
+  const int vpr = (int)(row_bytes / 16);
+  long long gx = (most * vpr + 255) / 256;
+  const long long cap = (148LL * 16 + n_peers - 1) / n_peers;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  k_push_rows<<<dim3((unsigned)gx, (unsigned)n_peers), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, vpr,
+                                                                                      vec_per_factor, tab);
+  DL_LAUNCH_CHECK();
+  return DL_OK;
+}
+
+extern "C" int dl_need_masks(const dl_graph* g_host, const uint8_t* kstar, const int32_t* halo_off, int n_parts,
+                             uint32_t* masks, dl_stream_t stream) {
+  if (!dl_graph_ok(g_host) || n_parts < 1 || n_parts > 16 || !halo_off || !masks) return DL_EINVAL;
+  if (g_host->N == 0) return DL_OK;
+  if (g_host->nnz > 0 && (!kstar || !g_host->erow)) return DL_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  DL_CUDA_TRY(cudaMemsetAsync(masks, 0, (size_t)n_parts * (size_t)g_host->N * sizeof(uint32_t), st));
+  if (g_host->nnz == 0) return DL_OK;
+  const DlGraphDev g = dl_graph_dev(g_host);
+  long long grid = (g.nnz + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  k_need_masks<<<(int)grid, 256, 0, st>>>(g, kstar, halo_off, n_parts, masks);
+  DL_LAUNCH_CHECK();
+  return DL_OK;
+}
+
 // enable stores from the current device into `peer_device`'s memory (idempotent)
 extern "C" int dl_enable_peer_access(int peer_device) {
   int cur = 0, can = 0;

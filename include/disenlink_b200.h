@@ -322,6 +322,37 @@ int dl_factor_bwd_gather_push(const dl_graph* g_host, const float* Z, const floa
 int dl_pair_score_bwd_push(const dl_graph* inc_host, const int32_t* inc_pair, const float* Z,
                            const float* H, const float* dS, int K, int d, float T, float* dZ, float* dH,
                            float* hub_ws, float* const* dH_peers, int n_peers, dl_stream_t stream);
+/* ---- halo exchange of a node-partitioned run ------------------------------------------------
+ * Rank-local storage: a rank keeps its own rows [0, n_own) of every per-node array followed by the halo
+ * rows [n_own, n_own + n_halo) -- the remote nodes its CSR columns and pair lists reference, grouped by
+ * owner -- and its CSR columns are local indices (dl_graph.N = n_own, row_base = 0).  Before a kernel
+ * reads halo rows their OWNERS push them: exactly the rows (or, for dH, the routed factor slices) the
+ * peer reads, straight into the peer's array over NVLink peer memory.  No collective library call, no
+ * reduction; the caller orders the ranks with a barrier after the pushes.
+ *
+ * dl_push_rows: for every peer q (descs_host[q], host array) and t in [0, n):
+ *     dst_q[(dst_idx ? dst_idx[t] : t)] = src[(src_idx ? src_idx[t] : t)]     rows of row_bytes bytes
+ * dst = device pointer into the peer's array (mapped with dl_ipc_open), already offset to the block that
+ * receives this rank's rows when dst_idx == NULL.  vec_per_factor > 0 and desc.mask != NULL: a row is
+ * K = row_bytes / (16 vec_per_factor) factor slices and only the slices k with bit k of mask[source row]
+ * set are sent (the routed slices of dH the peer's backward pass 1 gathers; the others are never read).
+ * row_bytes % 16 == 0, pointers 16-byte aligned, n_peers <= 15.  One launch for all peers. */
+typedef struct dl_push_desc {
+  void* dst;
+  const int32_t* src_idx;
+  const int32_t* dst_idx;
+  const uint32_t* mask;
+  int64_t n;
+} dl_push_desc;
+int dl_push_rows(const void* src, int64_t row_bytes, int vec_per_factor, const dl_push_desc* descs_host,
+                 int n_peers, dl_stream_t stream);
+/* Which factor slices of an owned row does each peer read?  By the symmetry of adjacency and routing, peer p
+ * gathers G[j, k] (j owned here) exactly when this rank holds an entry (j, i) routed to k with i owned by p.
+ * masks [n_parts][g.N] (device uint32, overwritten): bit k of masks[p][j] set accordingly.  halo_off
+ * [n_parts + 1] (device int32) = boundaries of the owners' blocks in the local column index space
+ * (halo_off[0] = n_own; an empty block for this rank itself).  Integer work (atomicOr), n_parts <= 16. */
+int dl_need_masks(const dl_graph* g_host, const uint8_t* kstar, const int32_t* halo_off, int n_parts,
+                  uint32_t* masks, dl_stream_t stream);
 /* cudaDeviceEnablePeerAccess(peer_device) for the current device; DL_EINVAL if the pair has no P2P path. */
 int dl_enable_peer_access(int peer_device);
 /* Map / unmap a peer process's allocation for kernels of the CURRENT device: handle = the 64 bytes of the

@@ -1,21 +1,31 @@
 """World-size-2 test of the node-partitioned orchestration (disenlink_b200/partition.py) on CPU.
 
-torch.distributed with the gloo backend; the CUDA kernels are replaced by a backend that calls
-the CPU oracle on the rank's owned rows, so what is under test is the host logic: partition
-bounds and padding, owned-entry selection, pair sharding, incidence ranges and the exchange
-sequence (six in-place all-gathers per step).  The partitioned result must equal the
-single-process oracle result bit for bit.
+torch.distributed with the gloo backend; the CUDA kernels are replaced by a backend that calls the
+CPU oracle on the rank's LOCAL graph, so what is under test is the host logic: nnz-balanced split
+points, owned-entry selection, the halo (remote columns + pair endpoints), the local index space and the
+remapped CSR / pair / incidence lists, the send lists both sides agree on, and the exchange sequence
+(Z, s, H for the pair endpoints, prob, dH, r) over the torch.distributed point-to-point path.
+The partitioned result must equal the single-process oracle result bit for bit.
 """
 import os
 import socket
 
 import numpy as np
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from disenlink_b200.partition import NodePartition, PartitionedLinkStep, owned_entries, pair_shard
+from disenlink_b200.partition import HaloPlan, NodePartition, PartitionedLinkStep, owned_entries, pair_shard
+
+
+class _LocalGraph:
+    """rowptr padded to n_tot rows (halo rows are empty) so the oracle sees a square local problem."""
+
+    def __init__(self, rowptr, col, n_own, n_tot):
+        rp = np.full(n_tot + 1, int(rowptr[-1]), np.int64)
+        rp[:n_own + 1] = rowptr.numpy()
+        self.rowptr, self.col = rp, col.numpy().astype(np.int32)
+        self.nnz, self.n_own, self.n_tot = int(self.col.size), n_own, n_tot
 
 
 class OracleBackend:
@@ -25,75 +35,87 @@ class OracleBackend:
         from oracle import oracle
         self.o = oracle
 
-    def build_graph(self, src, dst, part):
+    def build_csr(self, src, dst, part):
         rows, cols = owned_entries(src, dst, part)
-        key = np.unique((rows.numpy() + part.lo) * part.n_pad + cols.numpy())
-        r, c = key // part.n_pad, (key % part.n_pad).astype(np.int32)
-        rowptr = np.zeros(part.n_pad + 1, np.int64)          # global row ids; foreign rows stay empty
-        np.cumsum(np.bincount(r, minlength=part.n_pad), out=rowptr[1:])
+        key = np.unique(rows.numpy() * part.n_global + cols.numpy())
+        r, c = key // part.n_global, key % part.n_global
+        rowptr = np.zeros(part.n_local + 1, np.int64)
+        np.cumsum(np.bincount(r, minlength=part.n_local), out=rowptr[1:])
+        return torch.from_numpy(rowptr), torch.from_numpy(c.astype(np.int32))
 
-        class G:
-            pass
-        g = G()
-        g.rowptr, g.col, g.nnz, g.part = rowptr, c, int(c.size), part
-        return g
+    def make_graph(self, rowptr, col_local, n_own, n_tot):
+        return _LocalGraph(rowptr, col_local, n_own, n_tot)
 
-    def build_pairs(self, u, v, part):
-        P = int(u.numel())
-        per, p_lo, p_hi = pair_shard(P, part.world, part.rank)
+    def build_incidence(self, u, v, part):
+        un, vn = u.numpy(), v.numpy()
+        P = un.size
+        node = np.stack([un, vn], 1).reshape(-1)                # incidence 2p = u side, 2p + 1 = v side
+        other = np.stack([vn, un], 1).reshape(-1)
+        pair = np.repeat(np.arange(P), 2)
+        keep = (node >= part.lo) & (node < part.hi)
+        node, other, pair = node[keep] - part.lo, other[keep], pair[keep]
+        order = np.argsort(node, kind="stable")
+        ptr = np.zeros(part.n_local + 1, np.int64)
+        np.cumsum(np.bincount(node, minlength=part.n_local), out=ptr[1:])
+        return (torch.from_numpy(ptr), torch.from_numpy(other[order].astype(np.int32)),
+                torch.from_numpy(pair[order].astype(np.int32)))
 
+    def make_pairs(self, u_loc, v_loc, n_tot):
         class B:
             pass
-        shard = B()
-        shard.u, shard.v = u[p_lo:p_hi].numpy(), v[p_lo:p_hi].numpy()
-        inc = B()
-        inc.u, inc.v, inc.part = u.numpy(), v.numpy(), part
-        inc.nnz = int(((u >= part.lo) & (u < part.hi)).sum() + ((v >= part.lo) & (v < part.hi)).sum())
-        inc.n_hub = 0
-        return shard, inc, None
+        b = B()
+        b.u, b.v = u_loc.numpy(), v_loc.numpy()
+        return b
 
     def edge_attn_fwd(self, g, Z, T, kstar, w, s):
         ks, ww, ss = self.o.edge_attn_fwd(g.rowptr, g.col, Z.numpy(), T)
         kstar[:g.nnz] = torch.from_numpy(ks)
         w[:g.nnz] = torch.from_numpy(ww)
-        s[g.part.lo:g.part.hi] = torch.from_numpy(ss[g.part.lo:g.part.hi])
+        s[:g.n_own] = torch.from_numpy(ss[:g.n_own])
 
     def factor_spmm_fwd(self, g, Z, kstar, w, s, beta, H, sj=None, zs=None):
         out = self.o.factor_spmm_fwd(g.rowptr, g.col, Z.numpy(), kstar[:g.nnz].numpy(), w[:g.nnz].numpy(),
                                      s.numpy(), beta)
-        H[g.part.lo:g.part.hi] = torch.from_numpy(out[g.part.lo:g.part.hi])
+        H[:g.n_own] = torch.from_numpy(out[:g.n_own])
 
     def pair_score_fwd(self, Z, H, shard, T, prob_slice):
         _, prob = self.o.pair_score_fwd(shard.u, shard.v, Z.numpy(), H.numpy(), T)
         prob_slice.copy_(torch.from_numpy(prob))
 
     def pair_score_bwd(self, inc, inc_pair, Z, H, dS, T, dZ, dH):
-        P = inc.u.size
-        a, b = self.o.pair_score_bwd(inc.u, inc.v, Z.numpy(), H.numpy(), dS[:P].numpy(), T)
-        lo, hi = inc.part.lo, inc.part.hi
-        dZ[lo:hi] = torch.from_numpy(a[lo:hi])
-        dH[lo:hi] = torch.from_numpy(b[lo:hi])
+        # one-sided: the `other` endpoints are shifted into a shadow copy of the arrays, so only the owned
+        # endpoint of every incidence receives its term
+        n_own, n_tot = inc.n_own, inc.n_tot
+        rows = np.repeat(np.arange(n_own), np.diff(inc.rowptr[:n_own + 1]))
+        Z2, H2 = np.concatenate([Z.numpy()] * 2), np.concatenate([H.numpy()] * 2)
+        a, b = self.o.pair_score_bwd(rows, inc.col.astype(np.int64) + n_tot, Z2, H2,
+                                     dS.numpy()[inc_pair.numpy()], T)
+        dZ[:n_own] = torch.from_numpy(a[:n_own])
+        dH[:n_own] = torch.from_numpy(b[:n_own])
 
     def link_bce(self, prob, labels, weights, dS):
         loss, ds = self.o.bce_weighted(prob.numpy(), labels.numpy(), weights.numpy())
         dS.copy_(torch.from_numpy(ds))
         return torch.tensor(loss, dtype=torch.float32)
 
-    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r, peers=None, x=None):
-        lo, hi = g.part.lo, g.part.hi
-        dz, rr = dZ.numpy().copy(), np.zeros(tuple(r.shape), np.float32)
+    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r, x=None):
+        n = g.n_own
+        dz = np.zeros((g.n_tot,) + tuple(dZ.shape[1:]), np.float32)
+        dz[:n] = dZ.numpy()
+        rr = np.zeros(tuple(r.shape), np.float32)
         self.o.factor_bwd_gather(g.rowptr, g.col, Z.numpy(), G.numpy(), kstar[:g.nnz].numpy(),
                                  w[:g.nnz].numpy(), s.numpy(), beta, dz, rr)
-        dZ[lo:hi] = torch.from_numpy(dz[lo:hi])
-        r[lo:hi] = torch.from_numpy(rr[lo:hi])
+        dZ.copy_(torch.from_numpy(dz[:n]))
+        r[:n] = torch.from_numpy(rr[:n])
         return False                                   # x (per-entry dots for pass 2) not filled
 
     def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ, sj=None, x=None):
         assert x is None
-        lo, hi = g.part.lo, g.part.hi
-        dz = dZ.numpy().copy()
+        n = g.n_own
+        dz = np.zeros((g.n_tot,) + tuple(dZ.shape[1:]), np.float32)
+        dz[:n] = dZ.numpy()
         self.o.factor_bwd_edges(g.rowptr, g.col, Z.numpy(), G.numpy(), s.numpy(), r.numpy(), beta, T, dz)
-        dZ[lo:hi] = torch.from_numpy(dz[lo:hi])
+        dZ.copy_(torch.from_numpy(dz[:n]))
 
 
 def make_inputs(n=203, e=1500, K=3, d=8, P=901, seed=0):
@@ -114,9 +136,9 @@ def run_step(world, rank, group=None):
     step = PartitionedLinkStep(src, dst, n, u, v, lab, wts, K, d, 0.6, 1.0, world=world, rank=rank,
                                group=group, backend=OracleBackend(), device=torch.device("cpu"))
     part = step.part
-    Zf = torch.zeros(part.n_pad, K, d)
-    Zf[part.lo:part.hi] = Z[part.lo:part.hi]          # each rank only has its own rows before the gather
-    step.run(Zf)
+    step.Z_own.copy_(Z[part.lo:part.hi])              # each rank only has its own rows before the exchange
+    step.run()
+    step.run()                                        # a second step over the same buffers (ordering / WAR guard)
     return step, part
 
 
@@ -126,9 +148,12 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         step, part = run_step(world, rank)
-        torch.save({"dZ": step.dZ[part.lo:part.hi].clone(), "H": step.H.clone(), "prob": step.prob.clone(),
-                    "loss": step.loss.clone(), "lo": part.lo, "hi": part.hi, "s": step.s.clone(),
-                    "nnz": step.graph.nnz}, os.path.join(out_dir, f"rank{rank}.pt"))
+        n = step.n_own
+        torch.save({"dZ": step.dZ.clone(), "H": step.H[:n].clone(), "prob": step.prob.clone(),
+                    "loss": step.loss.clone(), "lo": part.lo, "hi": part.hi, "s": step.s[:n].clone(),
+                    "r": step.r[:n].clone(), "nnz": step.graph.nnz, "n_halo": step.plan.n_halo,
+                    "halo": step.plan.halo.clone(), "Zhalo": step.Z[n:].clone(), "shalo": step.s[n:].clone(),
+                    "bounds": part.bounds}, os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -138,11 +163,34 @@ def test_partition_bounds():
         parts = [NodePartition(n, world, r) for r in range(world)]
         assert parts[0].lo == 0 and parts[-1].hi == n
         assert all(a.hi == b.lo for a, b in zip(parts[:-1], parts[1:]))
-        assert all(p.n_pad == p.per * world >= n for p in parts)
-        cover = sum(p.n_local for p in parts)
-        assert cover == n
+        assert sum(p.n_local for p in parts) == n
     per, lo, hi = pair_shard(10, 4, 3)
     assert (per, lo, hi) == (3, 9, 10)
+
+
+def test_nnz_balanced_split_points():
+    """Power-law degrees: equal node ranges are badly unbalanced, the degree-prefix split is not."""
+    rng = np.random.default_rng(0)
+    n, e, world = 20000, 300000, 8
+    ids = (rng.random(e) ** 3 * n).astype(np.int64)            # hubs at the low ids (no shuffle: worst case)
+    src, dst = torch.from_numpy(ids), torch.from_numpy(rng.integers(0, n, e))
+    parts = [NodePartition.nnz_balanced(src, dst, n, world, r) for r in range(world)]
+    assert parts[0].lo == 0 and parts[-1].hi == n and all(a.hi == b.lo for a, b in zip(parts[:-1], parts[1:]))
+    assert all(p.bounds == parts[0].bounds for p in parts)
+
+    def load(ps):
+        return [int(owned_entries(src, dst, p)[0].numel()) for p in ps]
+    bal, eq = load(parts), load([NodePartition(n, world, r) for r in range(world)])
+    assert max(bal) < 1.1 * (sum(bal) / world)
+    assert max(eq) > 2.0 * (sum(eq) / world)
+
+
+def test_halo_plan_single_rank_is_identity():
+    part = NodePartition(10, 1, 0)
+    plan = HaloPlan(part, torch.empty(0, dtype=torch.int64), torch.empty(0, dtype=torch.int64))
+    assert plan.n_tot == 10 and plan.n_halo == 0
+    ids = torch.tensor([0, 3, 9])
+    assert torch.equal(plan.to_local(ids), ids)
 
 
 def test_two_rank_gloo_equals_single_process(tmp_path):
@@ -152,12 +200,17 @@ def test_two_rank_gloo_equals_single_process(tmp_path):
         port = sk.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     outs = [torch.load(os.path.join(tmp_path, f"rank{r}.pt")) for r in range(2)]
-    n = part1.n_global
+    assert outs[0]["bounds"] == outs[1]["bounds"]
     assert sum(o["nnz"] for o in outs) == single.graph.nnz
+    assert all(0 < o["n_halo"] < part1.n_global for o in outs)          # rank-local storage: own + halo only
     dZ = torch.cat([o["dZ"] for o in outs])
-    assert torch.equal(dZ, single.dZ[:n])
+    assert torch.equal(dZ, single.dZ)
+    assert torch.equal(torch.cat([o["H"] for o in outs]), single.H)
+    assert torch.equal(torch.cat([o["s"] for o in outs]), single.s)
+    assert torch.equal(torch.cat([o["r"] for o in outs]), single.r)
     for o in outs:
-        assert torch.equal(o["H"][:n], single.H[:n])
-        assert torch.equal(o["s"][:n], single.s[:n])
         assert torch.equal(o["prob"][:single.P], single.prob[:single.P])
         assert torch.equal(o["loss"], single.loss)
+        # the halo rows hold exactly the owners' values
+        assert torch.equal(o["Zhalo"], single.Z[o["halo"]])
+        assert torch.equal(o["shalo"], single.s[o["halo"]])
