@@ -418,8 +418,8 @@ int dl_edge_attn_fwd_push(const dl_graph* g_host, const float* Z, int K, int d, 
 
 static int spmm_fwd_impl(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
                          const float* w, const float* s, int K, int d, float beta,
-                         float one_minus_beta, float* H, float* sj_out, float* zs_scratch, float* hub_ws,
-                         float* const* H_peers, int n_peers, dl_stream_t stream) {
+                         float one_minus_beta, float* H, float* sj_out, float* zs_scratch, int64_t zs_rows,
+                         float* hub_ws, float* const* H_peers, int n_peers, dl_stream_t stream) {
   if (!dl_graph_ok(g_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
   if (g_host->N == 0) return DL_OK;
   if (!Z || !s || !H || (g_host->nnz > 0 && (!kstar || !w))) return DL_EINVAL;
@@ -433,7 +433,7 @@ static int spmm_fwd_impl(const dl_graph* g_host, const float* Z, const uint8_t* 
   // pre-scaled path: needs every gathered row inside [0, N) (a graph that is not row-partitioned)
   if (zs_scratch && (sj_out || g.row_base != 0)) return DL_EINVAL;
   if (zs_scratch && g.nnz > 0 && d % 4 == 0 && g.erow && !(flags & (DL_F_NO_STREAM | DL_F_NO_PRESCALE))) {
-    k_scale_rows<<<148 * 16, 256, 0, st>>>(Z, s, g.N, K, d, zs_scratch);
+    k_scale_rows<<<148 * 16, 256, 0, st>>>(Z, s, zs_rows > g.N ? zs_rows : g.N, K, d, zs_scratch);
     DL_LAUNCH_CHECK();
     rc = dl_launch_gather_stream(0, g, Z, zs_scratch, kstar, w, nullptr, K, d, beta, one_minus_beta, H, nullptr,
                                  hub_ws, st);
@@ -476,17 +476,17 @@ static int spmm_fwd_impl(const dl_graph* g_host, const float* Z, const uint8_t* 
 
 int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
                        const float* w, const float* s, int K, int d, float beta,
-                       float one_minus_beta, float* H, float* sj_out, float* zs_scratch, float* hub_ws,
-                       dl_stream_t stream) {
-  return spmm_fwd_impl(g_host, Z, kstar, w, s, K, d, beta, one_minus_beta, H, sj_out, zs_scratch, hub_ws, nullptr, 0,
-                       stream);
+                       float one_minus_beta, float* H, float* sj_out, float* zs_scratch, int64_t zs_rows,
+                       float* hub_ws, dl_stream_t stream) {
+  return spmm_fwd_impl(g_host, Z, kstar, w, s, K, d, beta, one_minus_beta, H, sj_out, zs_scratch, zs_rows, hub_ws,
+                       nullptr, 0, stream);
 }
 
 int dl_factor_spmm_fwd_push(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
                             const float* w, const float* s, int K, int d, float beta,
                             float one_minus_beta, float* H, float* sj_out, float* hub_ws,
                             float* const* H_peers, int n_peers, dl_stream_t stream) {
-  return spmm_fwd_impl(g_host, Z, kstar, w, s, K, d, beta, one_minus_beta, H, sj_out, nullptr, hub_ws, H_peers,
+  return spmm_fwd_impl(g_host, Z, kstar, w, s, K, d, beta, one_minus_beta, H, sj_out, nullptr, 0, hub_ws, H_peers,
                        n_peers, stream);
 }
 

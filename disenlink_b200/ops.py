@@ -79,8 +79,8 @@ def factor_spmm_fwd(graph: Graph, Z, kstar, w, s, beta: float, out=None, sj=None
     per entry (pass it on to factor_bwd / factor_bwd_edges).  `zs` = optional [N,K,d] scratch: the
     kernel then gathers slices pre-divided by s (one DRAM transaction per entry instead of two); only
     for graphs that are not row-partitioned, and exclusive with `sj`."""
-    if zs is not None and (sj is not None or graph.row_base != 0 or graph.n_global != graph.N):
-        raise ValueError("zs needs a graph that is not row-partitioned and excludes sj")
+    if zs is not None and (sj is not None or graph.row_base != 0):
+        raise ValueError("zs needs row_base == 0 (one GPU or a rank-local index space) and excludes sj")
     K, d = _check_Z(Z, graph.n_global)
     Z = Z.contiguous()
     dev = Z.device
@@ -88,6 +88,7 @@ def factor_spmm_fwd(graph: Graph, Z, kstar, w, s, beta: float, out=None, sj=None
         H = torch.empty_like(Z) if out is None else out
         check(lib().dl_factor_spmm_fwd(graph.ref, ptr(Z), ptr(kstar), ptr(w), ptr(s), K, d,
                                        float(beta), one_minus(beta), ptr(H), _optr(sj), _optr(zs),
+                                       int(Z.shape[0]) if zs is not None else 0,
                                        ptr(graph.hub_scratch(K * d)), stream_of(dev)),
               "dl_factor_spmm_fwd")
     return H
@@ -257,7 +258,7 @@ def _spmm_side_buffers(graph: Graph, Z, need_grad: bool):
     """-> (sj, zs) for factor_spmm_fwd.  A graph that is not row-partitioned gets the pre-scaled path
     (zs: a transient [N,K,d] scratch; halves the DRAM transactions of the aggregation); a partitioned
     one keeps s[col,kstar] per entry for the backward instead (sj)."""
-    if graph.row_base == 0 and graph.n_global == graph.N and graph.nnz > 0:
+    if graph.row_base == 0 and graph.nnz > 0:
         return None, torch.empty_like(Z)
     if need_grad:
         return torch.empty(max(graph.nnz, 1), dtype=torch.float32, device=Z.device), None

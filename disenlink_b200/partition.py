@@ -507,9 +507,10 @@ class PartitionedLinkStep:
         nnz = self.graph.nnz
         self.kstar = torch.empty(max(nnz, 1), dtype=torch.uint8, device=dev)
         self.w = torch.empty(max(nnz, 1), **f32)
-        # one rank: the aggregation gathers slices pre-divided by s (scratch = the dH buffer, idle during
-        # the forward); several ranks: s[col, kstar] per local entry goes forward -> pass 2
-        self.prescale = (world == 1) and not (getattr(self.graph, "flags", 0) & 8)    # _lib.DL_F_NO_PRESCALE
+        # the aggregation gathers slices pre-divided by s (scratch = the dH buffer, idle during the forward;
+        # own and halo rows alike: s of the halo has been pushed by then); with DL_F_NO_PRESCALE it gathers
+        # s[col, kstar] per entry and hands the per-entry copy to pass 2
+        self.prescale = hasattr(be, "entry_scratch") and not (getattr(self.graph, "flags", 0) & 8)
         self.sj = None if self.prescale else torch.empty(max(nnz, 1), **f32)
         # <G[j,k*], Z[i,k*]> per entry, pass 1 -> pass 2 (the graph's per-entry scratch, shared with the
         # symmetric attention's packed records, which are dead by then)

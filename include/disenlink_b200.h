@@ -175,15 +175,16 @@ int dl_edge_attn_fwd_sym(const dl_graph* g_host, const dl_graph* upper_host, con
  * one_minus_beta is passed separately because Python evaluates (1 - beta) in double.
  * sj_out (may be NULL): per-entry copy sj[e] = s[col[e], kstar[e]] of the normaliser the kernel
  * gathers anyway; handing it to dl_factor_bwd(_edges) saves the backward one gather per entry.
- * zs_scratch (may be NULL): N*K*d floats of scratch.  When given, Z / s is written there in one
- * streaming pass and the kernel gathers pre-normalised slices: one DRAM transaction per entry
- * instead of two (slice + s[col,k]).  Only for graphs that are not row-partitioned (row_base == 0,
- * every column < N), and exclusive with sj_out (DL_EINVAL otherwise).
+ * zs_scratch (may be NULL): zs_rows*K*d floats of scratch, zs_rows = number of rows of Z and s (every
+ * column index is below it; 0 = g.N).  When given, Z / s is written there in one streaming pass and the
+ * kernel gathers pre-normalised slices: one DRAM transaction per entry instead of two (slice +
+ * s[col,k]).  Needs row_base == 0 (one GPU, or the rank-local index space of a partitioned run, where
+ * the rows beyond g.N are the halo) and is exclusive with sj_out (DL_EINVAL otherwise).
  * hub_ws: dl_hub_scratch_floats(g, K*d) floats. */
 int dl_factor_spmm_fwd(const dl_graph* g_host, const float* Z, const uint8_t* kstar,
                        const float* w, const float* s, int K, int d, float beta,
-                       float one_minus_beta, float* H, float* sj_out, float* zs_scratch, float* hub_ws,
-                       dl_stream_t stream);
+                       float one_minus_beta, float* H, float* sj_out, float* zs_scratch, int64_t zs_rows,
+                       float* hub_ws, dl_stream_t stream);
 
 /* (4) backward of (2)+(3) w.r.t. Z given G = dL/dH.  dZ is ACCUMULATED into (it may already
  * hold the decoder's direct gradient); r [N,K] is scratch/output.  Closed form in DESIGN.md.
