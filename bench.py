@@ -528,7 +528,7 @@ def gen_pairs_from_edges(src, dst, N, E, P, dev):
 # ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
-PHASES = ["ag_Z", "attn_fwd", "ag_s", "spmm_fwd", "ag_H", "pair_fwd", "ag_prob", "loss", "pair_bwd",
+PHASES = ["wait", "ag_Z", "attn_fwd", "ag_s", "spmm_fwd", "ag_H", "pair_fwd", "ag_prob", "loss", "pair_bwd",
           "ag_dH", "bwd_gather", "ag_r", "bwd_edges"]
 KERNEL_PHASES = ["attn_fwd", "spmm_fwd", "pair_fwd", "pair_bwd", "bwd_gather", "bwd_edges"]
 
@@ -623,8 +623,12 @@ def run_native(args):
             phase_ms[n1] += e0.elapsed_time(e1)
     phase_ms = {p: v / args.steps for p, v in phase_ms.items()}
     loss_val = float(step.loss.item())
+    per_rank = None
     if world > 1:
         tt = torch.tensor([total_ms] + [phase_ms[p] for p in PHASES], dtype=torch.float64, device=dev)
+        allt = [torch.empty_like(tt) for _ in range(world)]
+        dist.all_gather(allt, tt)
+        per_rank = {p: [round(float(a[1 + i]), 3) for a in allt] for i, p in enumerate(PHASES)}
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt[0].item())
         phase_ms = {p: float(x) for p, x in zip(PHASES, tt[1:].tolist())}
@@ -632,7 +636,7 @@ def run_native(args):
     t_factor = phase_ms["attn_fwd"] + phase_ms["spmm_fwd"] + phase_ms["bwd_gather"] + phase_ms["bwd_edges"]
     # the same definition at every N: the four factor kernels plus the exchanges THEY need (Z, s, the routed
     # dH slices, r; all zero on one GPU).  The H and prob exchanges serve the pair scoring and count there.
-    t_comm_factor = phase_ms["ag_Z"] + phase_ms["ag_s"] + phase_ms["ag_dH"] + phase_ms["ag_r"]
+    t_comm_factor = phase_ms["wait"] + phase_ms["ag_Z"] + phase_ms["ag_s"] + phase_ms["ag_dH"] + phase_ms["ag_r"]
     value = nnz_global / ((t_factor + t_comm_factor) * 1e-3)
     pair_rate = P / ((phase_ms["pair_fwd"] + phase_ms["ag_H"] + phase_ms["ag_prob"]) * 1e-3)
 
@@ -880,7 +884,7 @@ def run_native(args):
                        else f"node-partitioned x{world}, torch.distributed point-to-point halo exchange"),
                    "l2": f"inputs exceed L2: Z alone is {N * D * 4 / 2**30:.1f} GiB vs 126 MB L2 (no flush needed)",
                    "value_definition": "nnz / (attention + aggregation + both backward passes + the halo exchanges they "
-                                       "need: Z, s, routed dH slices, r -- zero on one GPU); the same at every N"},
+                                       "need: Z, s, routed dH slices, r, and the wait for the slowest rank -- all zero on one GPU); the same at every N"},
         "pair_scores_per_s": pair_rate,
         "phases_ms": {k: round(v, 4) for k, v in phase_ms.items()},
         "kernels": kernels, "roofline": roofline, "clocks": clocks,
@@ -893,6 +897,7 @@ def run_native(args):
         line["parity"] = parity
     if world > 1:
         line["partition"] = {"bounds": part.bounds, "rank0": volume}
+        line["phases_ms_per_rank"] = per_rank
     if extras is not None:
         line["next_rows"] = extras
     if cb is not None:

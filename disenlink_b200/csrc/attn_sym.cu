@@ -56,7 +56,8 @@ struct UpperCount {
 __global__ void k_sym_fill(const long long* __restrict__ rowptr, const int* __restrict__ col,
                            const int* __restrict__ erow, long long nnz, const long long* __restrict__ fu,
                            const long long* __restrict__ uptr, int* __restrict__ ucol, int* __restrict__ eidx,
-                           int* __restrict__ status, unsigned long long* __restrict__ n_diag) {
+                           int* __restrict__ lcol, int* __restrict__ lmirror, int* __restrict__ status,
+                           unsigned long long* __restrict__ n_diag) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
     const int i = erow[e], j = col[e];
@@ -72,11 +73,16 @@ __global__ void k_sym_fill(const long long* __restrict__ rowptr, const int* __re
         const long long mid = (a + b) >> 1;
         if (col[mid] < i) a = mid + 1; else b = mid;
       }
+      int t = 0;
       if (a < b0 && col[a] == i) {
-        eidx[e] = (int)(uptr[j] + (a - fu[j]));
+        t = (int)(uptr[j] + (a - fu[j]));
       } else {
-        eidx[e] = 0;
         *status = DL_EASYM;
+      }
+      eidx[e] = t;
+      if (lcol) {                                  // lower-triangle view: entry e is its (e - uptr[i])-th entry
+        lcol[e - uptr[i]] = j;
+        lmirror[e - uptr[i]] = t;
       }
     }
   }
@@ -210,8 +216,8 @@ size_t dl_sym_index_workspace_bytes(int64_t N) {
 }
 
 int dl_sym_index(const int64_t* rowptr, const int32_t* col, const int32_t* erow, int64_t N, int64_t nnz,
-                 int64_t* uptr, int32_t* ucol, int32_t* eidx, int32_t* status_out, void* ws, size_t ws_bytes,
-                 dl_stream_t stream) {
+                 int64_t* uptr, int32_t* ucol, int32_t* eidx, int32_t* lcol, int32_t* lmirror, int32_t* status_out,
+                 void* ws, size_t ws_bytes, dl_stream_t stream) {
   if (N < 0 || nnz < 0 || !rowptr || !uptr || !ws || (nnz > 0 && (!col || !erow))) return DL_EINVAL;
   if (ws_bytes < dl_sym_index_workspace_bytes(N)) return DL_EWORKSPACE;
   if (nnz >= 0x7fffffffLL) return DL_EUNSUPPORTED;       // positions in the upper view are int32
@@ -226,14 +232,14 @@ int dl_sym_index(const int64_t* rowptr, const int32_t* col, const int32_t* erow,
     return dlp::scan<false, long long>(UpperCount{(const long long*)rowptr, fu, N}, dlp::StoreArr<long long>{(long long*)uptr},
                                        N + 1, dlp::OpSum<long long>(), 0LL, scan_ws, st);
   }
-  if (!eidx || !status_out) return DL_EINVAL;
+  if (!eidx || !status_out || ((lcol == nullptr) != (lmirror == nullptr))) return DL_EINVAL;
   DL_CUDA_TRY(cudaMemsetAsync(status_out, 0, sizeof(int32_t), st));
   unsigned long long* n_diag =
       (unsigned long long*)((char*)ws + dlp::align256((size_t)(N + 1) * 8) + dlp::scan_ws_bytes(N + 1, 8));
   DL_CUDA_TRY(cudaMemsetAsync(n_diag, 0, sizeof(unsigned long long), st));
   if (nnz > 0) {
     k_sym_fill<<<blocks_for(nnz), 256, 0, st>>>((const long long*)rowptr, col, erow, nnz, fu, (const long long*)uptr,
-                                                ucol, eidx, status_out, n_diag);
+                                                ucol, eidx, lcol, lmirror, status_out, n_diag);
     DL_LAUNCH_CHECK();
     k_sym_check<<<1, 1, 0, st>>>(nnz, (const long long*)uptr, N, n_diag, status_out);
     DL_LAUNCH_CHECK();

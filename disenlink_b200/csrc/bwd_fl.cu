@@ -23,6 +23,16 @@
 #include "dl_stream.cuh"
 #include "dl_fl.cuh"
 
+// -DDL_DEBUG_SINGLE_WRITER: every direct row update claims the row in a per-launch counter array; the
+// launcher returns DL_EINTERNAL if any row was claimed twice.  The fire-and-forget reduction below is
+// only schedule-independent because each row has ONE direct writer per launch (rows cut by a range
+// boundary go through the carries); this build asserts it (tests/test_gpu_parity.py runs it when the
+// variant library tools/build_variant.sh produced is present).
+#ifdef DL_DEBUG_SINGLE_WRITER
+__device__ unsigned int* dl_dbg_claims = nullptr;
+__device__ unsigned int dl_dbg_violations = 0;
+#endif
+
 namespace {
 
 #ifndef FL_RING_N
@@ -39,9 +49,14 @@ namespace {
 #endif
 constexpr int FL_OWN = FL_OWN_N;     // staged own-row slots per stage; further rows of a step are read with plain loads
 
-// HAS_X: the per-entry dots <G[j,k*], Z[i,k*]> come from pass 1 (x array); no routed slice is staged
-template <int K_, int d_, bool HAS_X>
+// MODE 0: the routed slice G[j,k*] is staged and <G[j,k*], Z[i,k*]> computed here;
+// MODE 1 (HAS_X): the per-entry dots come from pass 1 (x array), no routed slice is staged;
+// MODE 2 (symmetric pass 2, phase A, see bwd_sym.cu): MODE 1 on the UPPER-triangle view of the graph
+//        (kstar and x in upper-view order, left there by pass 1), and the K coefficients of every entry
+//        are stored for the lower-triangle phase
+template <int K_, int d_, int MODE>
 struct FlCfg {
+  static constexpr bool HAS_X = MODE >= 1;
   static constexpr int FL_RING = HAS_X ? FL_RING_X : FL_RING_N;   // stages per warp ring (FL_RING - 1 in flight)
   static constexpr int K = K_, d = d_, D = K_ * d_;
   static constexpr int LPE = 8;                       // lanes per entry (factors padded to 8)
@@ -88,14 +103,15 @@ __device__ __forceinline__ float fl_dot(const float4 (&a)[C::C4], const float4 (
   return p[0];
 }
 
-template <int K_, int d_, bool HAS_X>
-__global__ void __launch_bounds__(FlCfg<K_, d_, HAS_X>::THREADS, 1)
+template <int K_, int d_, int MODE>
+__global__ void __launch_bounds__(FlCfg<K_, d_, MODE>::THREADS, 1)
 k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restrict__ G,
                const unsigned char* __restrict__ kstar, const float* __restrict__ s,
                const float* __restrict__ r, const float* __restrict__ sj, const float2* __restrict__ sr,
                const float* __restrict__ xc, float omb, float T, float* __restrict__ dZ,
-               float* __restrict__ carry) {
-  using C = FlCfg<K_, d_, HAS_X>;
+               float* __restrict__ carry, float* __restrict__ coef_out) {
+  using C = FlCfg<K_, d_, MODE>;
+  constexpr bool HAS_X = C::HAS_X;
   constexpr int K = C::K, d = C::d, D = C::D, LPE = C::LPE, EPS = C::EPS, QPC = C::QPC, C4 = C::C4;
   constexpr int FL_RING = C::FL_RING;
   constexpr int ROWS = C::ROWS, STAGE_B = C::STAGE_B, OWN_B = C::OWN_B;
@@ -227,6 +243,9 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
           // same value as load-add-store in any schedule -- without stalling on the load.  (f32
           // reductions flush subnormals to zero.)
           float* dst = dZ + (g.row_base + cur_row) * D + kap * d;
+#ifdef DL_DEBUG_SINGLE_WRITER
+          if (kap == 0 && atomicAdd(dl_dbg_claims + cur_row, 1u) != 0u) atomicAdd(&dl_dbg_violations, 1u);
+#endif
 #pragma unroll
           for (int c = 0; c < C4; ++c) fl_red_add4(dst + c * 4, dz[c]);
         }
@@ -349,6 +368,9 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
         const float ind = (kap == ks) ? 1.0f : 0.0f;
         float coef = __fmul_rn(basec, __fsub_rn(ind, __fmul_rn(ev, rsum)));
         coef = (valid && factive) ? coef : 0.0f;
+        // the coefficients are symmetric in (i, j): the lower-triangle phase reads them back instead of
+        // recomputing dots, exponentials and the softmax (32 contiguous bytes per entry at K = 8)
+        if (MODE == 2 && valid && factive) coef_out[(c * DL_CH + src) * K + kap] = coef;
         // accumulate: the whole step continues the current row (common), or run by run (entries of
         // a step are consecutive CSR entries)
         unsigned runs = (mA.smask >> (q * EPS)) & ((1u << EPS) - 1u);
@@ -381,25 +403,40 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
   dl_cp_async_wait<0>();
 }
 
-template <int K_, int d_, bool HAS_X>
+template <int K_, int d_, int MODE>
 struct FlLaunch {
   static int run(const DlGraphDev& g, const float* Z, const float* G, const unsigned char* kstar,
                  const float* s, const float* r, const float* sj, const float2* sr, const float* x, float omb,
-                 float T, float* dZ, float* carry, cudaStream_t st) {
-    using C = FlCfg<K_, d_, HAS_X>;
+                 float T, float* dZ, float* carry, cudaStream_t st, float* coef_out = nullptr) {
+    using C = FlCfg<K_, d_, MODE>;
     int dev = 0, sms = 0;
     DL_CUDA_TRY(cudaGetDevice(&dev));
     DL_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    DL_CUDA_TRY(cudaFuncSetAttribute(k_bwd_edges_fl<K_, d_, HAS_X>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DL_CUDA_TRY(cudaFuncSetAttribute(k_bwd_edges_fl<K_, d_, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)C::SMEM));
     const long long n_chunks = (g.nnz + DL_CH - 1) / DL_CH;
     const long long n_ranges = (n_chunks + DL_RANGE - 1) / DL_RANGE;
     long long grid = (n_ranges + C::NW - 1) / C::NW;
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
-    k_bwd_edges_fl<K_, d_, HAS_X><<<(int)grid, C::THREADS, C::SMEM, st>>>(g, Z, G, kstar, s, r, sj, sr, x, omb, T, dZ,
-                                                                          carry);
+#ifdef DL_DEBUG_SINGLE_WRITER
+    unsigned int* claims = nullptr;
+    const unsigned int zero = 0;
+    DL_CUDA_TRY(cudaMalloc(&claims, (size_t)g.N * sizeof(unsigned int)));
+    DL_CUDA_TRY(cudaMemsetAsync(claims, 0, (size_t)g.N * sizeof(unsigned int), st));
+    DL_CUDA_TRY(cudaMemcpyToSymbolAsync(dl_dbg_claims, &claims, sizeof(claims), 0, cudaMemcpyHostToDevice, st));
+    DL_CUDA_TRY(cudaMemcpyToSymbolAsync(dl_dbg_violations, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, st));
+#endif
+    k_bwd_edges_fl<K_, d_, MODE><<<(int)grid, C::THREADS, C::SMEM, st>>>(g, Z, G, kstar, s, r, sj, sr, x, omb, T, dZ,
+                                                                         carry, coef_out);
     DL_LAUNCH_CHECK();
+#ifdef DL_DEBUG_SINGLE_WRITER
+    unsigned int bad = 0;
+    DL_CUDA_TRY(cudaStreamSynchronize(st));
+    DL_CUDA_TRY(cudaMemcpyFromSymbol(&bad, dl_dbg_violations, sizeof(bad)));
+    DL_CUDA_TRY(cudaFree(claims));
+    if (bad) return DL_EINTERNAL;
+#endif
     return DL_OK;
   }
 };
@@ -435,12 +472,35 @@ int dl_launch_bwd_edges_fl(const DlGraphDev& g, const float* Z, const float* G, 
   int rc = -1000;
 #define FL_CASE(KK, DD)                                                                                             \
   if (K == KK && d == DD)                                                                                           \
-    rc = x ? FlLaunch<KK, DD, true>::run(g, Z, G, kstar, s, r, sj, sr, x, omb, T, dZ, scratch, st)                   \
-           : FlLaunch<KK, DD, false>::run(g, Z, G, kstar, s, r, sj, sr, nullptr, omb, T, dZ, scratch, st);
+    rc = x ? FlLaunch<KK, DD, 1>::run(g, Z, G, kstar, s, r, sj, sr, x, omb, T, dZ, scratch, st)                      \
+           : FlLaunch<KK, DD, 0>::run(g, Z, G, kstar, s, r, sj, sr, nullptr, omb, T, dZ, scratch, st);
   FL_CASE(8, 16)
   FL_CASE(8, 8)
   FL_CASE(5, 16)
 #undef FL_CASE
   if (rc != DL_OK) return rc;
   return dl_gather_chain_add(g, K, d, scratch, dZ, st);
+}
+
+// Symmetric pass 2, phase A: the kernel above on the upper-triangle view gu (entries with col >= row), kstar
+// and x in upper-view order (ku, xu); leaves the K coefficients of every upper entry in coef_out [nnz_u, K].
+// (s, r) must already be packed in sr.  Returns -1000 when (K, d) has no instantiation.
+int dl_launch_bwd_sym_upper(const DlGraphDev& gu, const float* Z, const float* G, const unsigned char* ku,
+                            const float* s, const float* r, const float2* sr, const float* xu, int K, int d, float omb,
+                            float T, float* dZ, float* coef_out, float* scratch, cudaStream_t st) {
+  if (!gu.erow || gu.nnz == 0 || !scratch || !dl_bwd_edges_fl_has(K, d) || !sr || !xu || !ku || !coef_out) return -1000;
+  int rc = -1000;
+#define FL_CASE(KK, DD) \
+  if (K == KK && d == DD) \
+    rc = FlLaunch<KK, DD, 2>::run(gu, Z, G, ku, s, r, nullptr, sr, xu, omb, T, dZ, scratch, st, coef_out);
+  FL_CASE(8, 16)
+  FL_CASE(8, 8)
+  FL_CASE(5, 16)
+#undef FL_CASE
+  if (rc != DL_OK) return rc;
+  return dl_gather_chain_add(gu, K, d, scratch, dZ, st);
+}
+
+void dl_pack_sr(const float* s, const float* r, long long n, float* sr_scratch, cudaStream_t st) {
+  k_pack_sr<<<148 * 8, 256, 0, st>>>(s, r, n, reinterpret_cast<float2*>(sr_scratch));
 }

@@ -209,6 +209,7 @@ const char* dl_error_string(int code) {
     case DL_ERANGE: return "index out of range";
     case DL_EASYM: return "adjacency pattern is not symmetric";
     case DL_EUNSUPPORTED: return "unsupported size";
+    case DL_EINTERNAL: return "internal invariant violated (debug build)";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
   }
 }

@@ -107,7 +107,8 @@ size_t dl_gather_stream_scratch_floats(long long nnz, int mode, int K, int d);
 int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const float* SRC,
                             const unsigned char* kstar, const float* w, const float* s, int K, int d,
                             float beta, float omb, float* OUT, float* r, float* scratch,
-                            cudaStream_t st, float* xout = nullptr);
+                            cudaStream_t st, float* xout = nullptr, const int* xidx = nullptr,
+                            unsigned char* ku_out = nullptr);
 // whether the streaming pass 1 of shape (K, d) leaves the per-entry dots in xout (needs d/4 a power of two)
 bool dl_gather_stream_has_x(int K, int d);
 int dl_gather_chain_add(const DlGraphDev& g, int K, int d, float* scratch, float* OUT, cudaStream_t st);

@@ -9,12 +9,14 @@
 // instruction moves one 512-byte row, completion tracked with commit / wait groups) while it
 // computes on the oldest stage.
 //
-// A warp-specialised variant (one producer warp per CTA issuing cp.async.bulk / TMA 1-D copies
-// into mbarrier-guarded stages, helpers below) was built and measured first: it is correct, but a
-// bulk copy takes uniform-register operands, so per-row copies are serialised (ncu: 8 UBLKCP per
-// 8-entry step in a loop), one producer warp tops out at ~17 rows/us, and the producers cost more
-// issue slots per entry than the vector cp.async issued by the consuming warp itself.  TMA pays for
-// large contiguous tiles, not for 512-byte random rows.
+// TMA was measured for this access pattern twice and is not used.  Round 1: a warp-specialised variant
+// (one producer warp per CTA issuing 1-D cp.async.bulk copies into mbarrier-guarded stages) -- a bulk
+// copy takes uniform-register operands, so per-row copies are serialised (ncu: 8 UBLKCP per 8-entry step),
+// one producer warp tops out at ~17 rows/us and costs more issue slots per entry than the vector cp.async
+// of the consuming warp.  Round 2: tools/gather_probe.cu times cp.async.bulk.tensor ... tile::gather4
+// (UTMALDG.2D.GATHER4, 4 rows per instruction) against ld.global / cp.async on random objects out of a
+// 25.6 GB array (profiles/r02_gather_probe.jsonl): 3.0e10 objects/s against 3.65e10 for objects <= 128 B,
+// the same 6.7-6.9 TB/s for 512-byte rows.  TMA pays for large contiguous tiles, not for random rows.
 //
 // Work decomposition (merge-path style): the CSR entries are cut into chunks of DL_CH consecutive
 // entries regardless of row boundaries; DL_RANGE consecutive chunks form a range owned by one
@@ -33,45 +35,6 @@
 
 __device__ __forceinline__ unsigned dl_smem_u32(const void* p) {
   return (unsigned)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void dl_mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dl_smem_u32(bar)), "r"(count));
-}
-
-__device__ __forceinline__ void dl_mbar_fence_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-__device__ __forceinline__ void dl_mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dl_smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void dl_mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dl_smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-
-__device__ __forceinline__ void dl_mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "DL_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DL_DONE_%=;\n"
-      "bra DL_WAIT_%=;\n"
-      "DL_DONE_%=:\n"
-      "}\n" ::"r"(dl_smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-
-// TMA 1-D bulk copy global -> shared, completion counted on `bar` (bytes must be a multiple of 16,
-// both addresses 16-byte aligned)
-__device__ __forceinline__ void dl_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes,
-                                            unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-                   "r"(dl_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(dl_smem_u32(bar))
-               : "memory");
 }
 
 // 16-byte cp.async global -> shared (LDGSTS), L2-only (.cg): gathered rows are not reused via L1
@@ -105,24 +68,5 @@ struct DlChunkStream {
     if (c1 % DL_RANGE != 0) return c1 < n_chunks ? c1 : -1;
     const long long rg = c / DL_RANGE + GW;      // first chunk of this warp's next range
     return rg < n_ranges ? rg * DL_RANGE : -1;
-  }
-};
-
-// geometry of the chunk / range / span decomposition of the warp-specialised variant
-struct DlSpanGeom {
-  long long n_chunks, n_ranges, n_spans;
-  __host__ __device__ static DlSpanGeom make(long long nnz, int nc) {
-    DlSpanGeom s;
-    s.n_chunks = (nnz + DL_CH - 1) / DL_CH;
-    s.n_ranges = (s.n_chunks + DL_RANGE - 1) / DL_RANGE;
-    s.n_spans = (s.n_ranges + nc - 1) / nc;
-    return s;
-  }
-  // chunk id handled by consumer w of span sp at step j, or -1
-  __device__ __forceinline__ long long chunk(long long sp, int nc, int w, int j) const {
-    const long long rg = sp * nc + w;
-    if (rg >= n_ranges) return -1;
-    const long long c = rg * DL_RANGE + j;
-    return c < n_chunks ? c : -1;
   }
 };

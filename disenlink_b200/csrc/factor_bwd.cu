@@ -387,8 +387,9 @@ extern "C" {
 
 static int bwd_gather_impl(const dl_graph* g_host, const float* Z, const float* G,
                            const uint8_t* kstar, const float* w, const float* s, int K, int d,
-                           float beta, float one_minus_beta, float* dZ, float* r, float* x, int* x_valid_out,
-                           float* hub_ws, float* const* r_peers, int n_peers, dl_stream_t stream) {
+                           float beta, float one_minus_beta, float* dZ, float* r, float* x, const int32_t* x_index,
+                           uint8_t* ku_out, int* x_valid_out, float* hub_ws, float* const* r_peers, int n_peers,
+                           dl_stream_t stream) {
   if (x_valid_out) *x_valid_out = 0;
   if (!dl_graph_ok(g_host) || !dl_shape_ok(K, d)) return DL_EINVAL;
   if (g_host->N == 0) return DL_OK;
@@ -403,7 +404,8 @@ static int bwd_gather_impl(const dl_graph* g_host, const float* Z, const float* 
   if (!(flags & DL_F_NO_STREAM)) {
     // the streaming pass 1 leaves x[e] = <G[j,k*], Z[i,k*]> for pass 2 when asked to
     float* xo = (x && !(flags & DL_F_NO_XDOT) && dl_gather_stream_has_x(K, d)) ? x : nullptr;
-    rc = dl_launch_gather_stream(1, g, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, hub_ws, st, xo);
+    rc = dl_launch_gather_stream(1, g, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, hub_ws, st, xo,
+                                 xo ? x_index : nullptr, (xo && x_index) ? ku_out : nullptr);
     if (rc == DL_OK && xo && x_valid_out) *x_valid_out = 1;
   }
   if (rc == DL_OK) return DL_OK;
@@ -438,18 +440,18 @@ static int bwd_gather_impl(const dl_graph* g_host, const float* Z, const float* 
 
 int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
                          const uint8_t* kstar, const float* w, const float* s, int K, int d,
-                         float beta, float one_minus_beta, float* dZ, float* r, float* x, int* x_valid_out,
-                         float* hub_ws, dl_stream_t stream) {
-  return bwd_gather_impl(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, x, x_valid_out, hub_ws,
-                         nullptr, 0, stream);
+                         float beta, float one_minus_beta, float* dZ, float* r, float* x, const int32_t* x_index,
+                         uint8_t* ku_out, int* x_valid_out, float* hub_ws, dl_stream_t stream) {
+  return bwd_gather_impl(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, x, x_index, ku_out,
+                         x_valid_out, hub_ws, nullptr, 0, stream);
 }
 
 int dl_factor_bwd_gather_push(const dl_graph* g_host, const float* Z, const float* G,
                               const uint8_t* kstar, const float* w, const float* s, int K, int d,
                               float beta, float one_minus_beta, float* dZ, float* r, float* x, int* x_valid_out,
                               float* hub_ws, float* const* r_peers, int n_peers, dl_stream_t stream) {
-  return bwd_gather_impl(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, x, x_valid_out, hub_ws,
-                         r_peers, n_peers, stream);
+  return bwd_gather_impl(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, x, nullptr, nullptr,
+                         x_valid_out, hub_ws, r_peers, n_peers, stream);
 }
 
 int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
@@ -506,8 +508,8 @@ int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const 
                   float* r, float* hub_ws, dl_stream_t stream) {
   if (!(T == T) || T == 0.0f) return DL_EINVAL;
   int x_valid = 0;
-  int rc = dl_factor_bwd_gather(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, x_scratch,
-                                &x_valid, hub_ws, stream);
+  int rc = dl_factor_bwd_gather(g_host, Z, G, kstar, w, s, K, d, beta, one_minus_beta, dZ, r, x_scratch, nullptr,
+                                nullptr, &x_valid, hub_ws, stream);
   if (rc) return rc;
   return dl_factor_bwd_edges(g_host, Z, G, kstar, w, s, r, sj, sr_scratch, n_nodes,
                              x_valid ? x_scratch : nullptr, K, d, one_minus_beta, T, dZ, hub_ws, stream);

@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(GS_WARPS * 32)
 k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restrict__ SRC,
                 const unsigned char* __restrict__ kstar, const float* __restrict__ w,
                 const float* __restrict__ s, float beta, float omb, float* __restrict__ OUT,
-                float* __restrict__ r, float* __restrict__ carry, float* __restrict__ xout) {
+                float* __restrict__ r, float* __restrict__ carry, float* __restrict__ xout,
+                const int* __restrict__ xidx, unsigned char* __restrict__ ku_out) {
   using C = GatherStreamCfg<M, MODE>;
   constexpr int K = M::K, d = M::d, D = M::D, NP = M::NP, L = M::L, LP = M::LP, FPP = M::FPP;
   constexpr int NG = 32 / LP, SLB = C::SLB, TILE_B = C::TILE_B;
@@ -437,7 +438,15 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
       }
     }
     __syncwarp();
-    if (MODE == 1 && want_x && mA.row >= 0) xout[c * DL_CH + lane] = xbuf[lane];
+    if (MODE == 1 && want_x && mA.row >= 0) {
+      // xidx (symmetric backward pass 2): only the entries with col >= row are needed, in upper-view order
+      if (xidx == nullptr) xout[c * DL_CH + lane] = xbuf[lane];
+      else if (mA.col >= mA.row) {
+        const int t = __ldg(xidx + c * DL_CH + lane);
+        xout[t] = xbuf[lane];
+        if (ku_out) ku_out[t] = (unsigned char)mA.ks;       // kstar in upper-view order, for phase A
+      }
+    }
     buf ^= 1;
     c = cn; cn = cnn;
     mA = mB; mB = mC;
@@ -450,7 +459,8 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
 template <class M, int MODE>
 int launch_gather_stream(const DlGraphDev& g, const float* Z, const float* SRC,
                          const unsigned char* kstar, const float* w, const float* s, float beta,
-                         float omb, float* OUT, float* r, float* carry, float* xout, cudaStream_t st) {
+                         float omb, float* OUT, float* r, float* carry, float* xout, const int* xidx,
+                         unsigned char* ku_out, cudaStream_t st) {
   using C = GatherStreamCfg<M, MODE>;
   if (C::SMEM > 200 * 1024) return -1000;
   if (C::SMEM > 48 * 1024)
@@ -469,7 +479,7 @@ int launch_gather_stream(const DlGraphDev& g, const float* Z, const float* SRC,
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   k_gather_stream<M, MODE><<<(int)grid, GS_WARPS * 32, C::SMEM, st>>>(g, Z, SRC, kstar, w, s, beta, omb, OUT,
-                                                                     r, carry, xout);
+                                                                     r, carry, xout, xidx, ku_out);
   DL_LAUNCH_CHECK();
   return DL_OK;
 }
@@ -495,7 +505,7 @@ size_t dl_gather_stream_scratch_floats(long long nnz, int mode, int K, int d) {
 int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const float* SRC,
                             const unsigned char* kstar, const float* w, const float* s, int K, int d,
                             float beta, float omb, float* OUT, float* r, float* scratch,
-                            cudaStream_t st, float* xout) {
+                            cudaStream_t st, float* xout, const int* xidx, unsigned char* ku_out) {
   if (!g.erow || g.nnz == 0 || !scratch) return -1000;
   const long long RE = (long long)DL_CH * DL_RANGE;
   const long long n_ranges = (g.nnz + RE - 1) / RE;
@@ -504,9 +514,9 @@ int dl_launch_gather_stream(int mode, const DlGraphDev& g, const float* Z, const
   float* chain = scratch + (size_t)n_ranges * 2 * W;
   int rc = -1000;
 #define BODY_MACRO(M)                                                                                       \
-  rc = (mode == 0)   ? launch_gather_stream<M, 0>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, nullptr, st)  \
-       : (mode == 1) ? launch_gather_stream<M, 1>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, xout, st)     \
-                     : launch_gather_stream<M, 2>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, nullptr, st);
+  rc = (mode == 0)   ? launch_gather_stream<M, 0>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, nullptr, nullptr, nullptr, st)  \
+       : (mode == 1) ? launch_gather_stream<M, 1>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, xout, xidx, ku_out, st)     \
+                     : launch_gather_stream<M, 2>(g, Z, SRC, kstar, w, s, beta, omb, OUT, r, carry, nullptr, nullptr, nullptr, st);
   DL_DISPATCH_SHAPES()
 #undef BODY_MACRO
   if (rc != DL_OK) return rc;

@@ -82,13 +82,27 @@ k_push_rows(const uint4* __restrict__ src, int vpr, int vpf, PushTable tab) {
   uint4* __restrict__ dst = reinterpret_cast<uint4*>(d.dst);
   const long long total = (long long)d.n * vpr;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long t = i / vpr;
-    const int c = (int)(i - t * vpr);
-    const long long sr = d.src_idx ? (long long)__ldg(d.src_idx + t) : t;
-    if (vpf > 0 && d.mask && !((__ldg(d.mask + sr) >> (c / vpf)) & 1u)) continue;
-    const long long dr = d.dst_idx ? (long long)__ldg(d.dst_idx + t) : t;
-    dst[dr * vpr + c] = __ldg(src + sr * vpr + c);
+  constexpr int U = 4;                       // independent 16-byte loads in flight per thread
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+    uint4 v[U];
+    long long di[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      di[u] = -1;
+      if (i < total) {
+        const long long t = i / vpr;
+        const int c = (int)(i - t * vpr);
+        const long long sr = d.src_idx ? (long long)__ldg(d.src_idx + t) : t;
+        if (vpf > 0 && d.mask && !((__ldg(d.mask + sr) >> (c / vpf)) & 1u)) continue;
+        const long long dr = d.dst_idx ? (long long)__ldg(d.dst_idx + t) : t;
+        di[u] = dr * vpr + c;
+        v[u] = __ldg(src + sr * vpr + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (di[u] >= 0) dst[di[u]] = v[u];
   }
 }
 

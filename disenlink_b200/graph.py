@@ -44,6 +44,7 @@ class Graph:
         self.nnz = int(col.numel())
         self._rev = None
         self._sym = None                      # (upper Graph, eidx) | False (pattern not symmetric / unavailable)
+        self._sym_lower = None
         self.sym_min_nnz = self.SYM_MIN_NNZ
         self._flags = _lib.default_flags()
         self._build_items()
@@ -211,20 +212,32 @@ class Graph:
                     uptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
                     status = torch.zeros(1, dtype=torch.int32, device=dev)
                     check(L.dl_sym_index(ptr(self.rowptr), ptr(self.col), ptr(self.erow), N, self.nnz, ptr(uptr),
-                                         None, None, None, ptr(ws), ws_bytes, stream_of(dev)), "dl_sym_index(count)")
+                                         None, None, None, None, None, ptr(ws), ws_bytes, stream_of(dev)),
+                          "dl_sym_index(count)")
                     nnz_u = int(uptr[-1].item())
+                    nnz_l = self.nnz - nnz_u
                     ucol = torch.empty(max(nnz_u, 1), dtype=torch.int32, device=dev)
                     eidx = torch.empty(self.nnz, dtype=torch.int32, device=dev)
+                    lcol = torch.empty(max(nnz_l, 1), dtype=torch.int32, device=dev)
+                    lmirror = torch.empty(max(nnz_l, 1), dtype=torch.int32, device=dev)
                     check(L.dl_sym_index(ptr(self.rowptr), ptr(self.col), ptr(self.erow), N, self.nnz, ptr(uptr),
-                                         ptr(ucol), ptr(eidx), ptr(status), ptr(ws), ws_bytes, stream_of(dev)),
-                          "dl_sym_index(fill)")
+                                         ptr(ucol), ptr(eidx), ptr(lcol), ptr(lmirror), ptr(status), ptr(ws), ws_bytes,
+                                         stream_of(dev)), "dl_sym_index(fill)")
                     ok = int(status.item()) == 0
                     del ws
                 if ok:
                     upper = Graph(uptr, ucol[:nnz_u], N)
                     upper._sym = False
+                    lower = Graph(self.rowptr - uptr, lcol[:nnz_l], N)        # strictly-lower entries, same row order
+                    lower._sym = False
                     self._sym = (upper, eidx)
+                    self._sym_lower = (lower, lmirror[:nnz_l])
         return self._sym or None
+
+    def sym_lower_view(self):
+        """-> (strictly-lower-triangle Graph, lmirror int32 [nnz_l] = upper-view position of every lower entry's
+        mirror) for the symmetric backward pass 2, or None (see sym_view)."""
+        return self._sym_lower if self.sym_view() is not None else None
 
     def rows(self) -> torch.Tensor:
         """Row id of every entry (torch op; for tests and dense views)."""

@@ -24,6 +24,7 @@ There is no CPU implementation: inputs must live on a CUDA device.
 """
 from __future__ import annotations
 
+import weakref
 from typing import List, Optional, Union
 
 import torch
@@ -100,7 +101,8 @@ class _GraphCache:
     and its work items are built once per distinct adjacency tensor."""
 
     def __init__(self):
-        self._key = None
+        self._ref = None                       # weakref to the tensor the cached graph was built from
+        self._version = None
         self._graph: Optional[Graph] = None
 
     def get(self, adj: AdjLike, n_nodes: int) -> Graph:
@@ -108,12 +110,15 @@ class _GraphCache:
             return adj
         if not isinstance(adj, torch.Tensor):
             raise TypeError("adj must be a dense [N,N] tensor, an edge_index [2,E] tensor or a Graph")
-        key = (adj.data_ptr(), adj._version, tuple(adj.shape), adj.dtype, adj.device)
-        if key != self._key:
+        # keyed on the tensor OBJECT (a weak reference) and its version counter: an address is not an
+        # identity -- the caching allocator hands a freed adjacency's address to the next one of that shape
+        same = self._ref is not None and self._ref() is adj and self._version == adj._version
+        if not same:
             require_cuda(adj, "adj")
-            if adj.is_sparse:
-                adj = adj.coalesce()
-                idx = adj.indices()[:, adj.values() != 0]
+            sparse = adj.layout != torch.strided        # checked before anything touches data_ptr()
+            if sparse:
+                coo = (adj.to_sparse_coo() if adj.layout != torch.sparse_coo else adj).coalesce()
+                idx = coo.indices()[:, coo.values() != 0]
                 rp_graph = _graph_from_entries(idx[0], idx[1], n_nodes)
             elif adj.dim() == 2 and adj.shape[0] == 2 and not adj.is_floating_point():
                 rp_graph = Graph.from_edge_index(adj, n_nodes)
@@ -121,7 +126,7 @@ class _GraphCache:
                 rp_graph = Graph.from_dense(adj)
             else:
                 raise ValueError(f"cannot interpret adj of shape {tuple(adj.shape)} for N={n_nodes}")
-            self._key, self._graph = key, rp_graph
+            self._ref, self._version, self._graph = weakref.ref(adj), adj._version, rp_graph
         return self._graph
 
 
@@ -136,7 +141,7 @@ def _graph_from_entries(row, col, n_nodes):
 
 
 def is_dense_adj(adj: AdjLike, n_nodes: int) -> bool:
-    return (isinstance(adj, torch.Tensor) and not adj.is_sparse and adj.dim() == 2
+    return (isinstance(adj, torch.Tensor) and adj.layout == torch.strided and adj.dim() == 2
             and adj.shape[0] == adj.shape[1] == n_nodes and (adj.is_floating_point() or n_nodes != 2))
 
 

@@ -98,7 +98,7 @@ def _x_scratch(graph: Graph, n_floats: int = 0):
     """Per-entry fp32 scratch cached on the graph handle: pass 1 of the backward leaves
     <G[j,k*], Z[i,k*]> per entry there for pass 2 (nnz floats); the symmetric attention keeps its
     packed (w, kstar) records of the upper-triangle entries there during the forward (2 nnz_u floats)."""
-    need = max(graph.nnz, int(n_floats), 1)
+    need = max(graph.nnz + graph.N + 8, int(n_floats), 1)       # 2 nnz_u = nnz + #self-loops <= nnz + N
     buf = getattr(graph, "_x_scratch", None)
     if buf is None or buf.numel() < need:
         buf = torch.empty(need, dtype=torch.float32, device=graph.device)
@@ -106,26 +106,62 @@ def _x_scratch(graph: Graph, n_floats: int = 0):
     return buf
 
 
-def factor_bwd_gather(graph: Graph, Z, G, kstar, w, s, beta: float, dZ, r, x=None, peers=None):
+def bwd_plan(graph: Graph, K: int, d: int, allow_sym: bool = True) -> dict:
+    """How the two backward passes of one step talk to each other.
+      mode "sym"   (symmetric, not row-partitioned graphs with a factor-per-lane kernel): pass 1 leaves
+                   <G[j,k*], Z[i,k*]> and kstar of the entries with col >= row in upper-view order, pass 2
+                   evaluates every undirected edge once (dl_factor_bwd_edges_sym); needs nnz_u*K floats of
+                   transient scratch -- when that does not fit, mode "x" is used
+      mode "x"     pass 1 leaves the per-entry dots for every entry, pass 2 reads them (dl_factor_bwd_edges)
+    The per-entry scratch is the graph's cached one (shared with the symmetric attention's packed records,
+    which are dead by the time the backward runs)."""
+    plan = {"mode": "x", "x": _x_scratch(graph), "x_valid": False}
+    f = graph.flags
+    if (allow_sym and graph.nnz >= graph.sym_min_nnz and graph.nnz > 0 and
+            not (f & (_lib.DL_F_NO_SYM | _lib.DL_F_NO_STREAM | _lib.DL_F_NO_FL | _lib.DL_F_NO_XDOT)) and
+            lib().dl_factor_bwd_edges_sym_supported(K, d) and graph.sym_view() is not None):
+        upper, eidx = graph.sym_view()
+        lower, lmirror = graph.sym_lower_view()
+        nu = upper.nnz
+        try:
+            coef = torch.empty(max(nu * K, 1), dtype=torch.float32, device=graph.device)
+        except torch.cuda.OutOfMemoryError:
+            return plan
+        scr = _x_scratch(graph, nu + (nu + 3) // 4 + 1)
+        plan.update(mode="sym", xu=scr[:nu], ku=scr[nu:nu + (nu + 3) // 4 + 1].view(torch.uint8), coef=coef,
+                    upper=upper, eidx=eidx, lower=lower, lmirror=lmirror)
+    return plan
+
+
+def factor_bwd_gather(graph: Graph, Z, G, kstar, w, s, beta: float, dZ, r, plan: dict = None, peers=None):
     """Pass 1 of the backward: r [N,K] and dZ += beta*G + T_ (see csrc/factor_bwd.cu).
-    `x` = optional f32 [nnz] buffer for the per-entry dots pass 2 can reuse; -> True when it was
-    filled (hand it to factor_bwd_edges only then).  `peers` = ctypes array of the peers' copies of r
-    (node-partitioned runs: the all-gather of r rides on the kernel)."""
+    `plan` = bwd_plan(...) (None: no per-entry dots are kept, pass 2 re-gathers the G slices); its "x_valid"
+    is set when the dots were filled.  `peers` = ctypes array of the peers' copies of r (replicated layout:
+    the all-gather of r rides on the kernel)."""
     K, d = _check_Z(Z, graph.n_global)
     dev = Z.device
     x_valid = ctypes.c_int(0)
+    x = xi = ku = None
+    if plan is not None:
+        if plan["mode"] == "sym":
+            x, xi, ku = plan["xu"], plan["eidx"], plan["ku"]
+        else:
+            x = plan["x"]
     with torch.cuda.device(dev):
         if peers is None:
             check(lib().dl_factor_bwd_gather(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d,
-                                             float(beta), one_minus(beta), ptr(dZ), ptr(r), _optr(x),
-                                             ctypes.byref(x_valid), ptr(graph.hub_scratch(K * d)),
+                                             float(beta), one_minus(beta), ptr(dZ), ptr(r), _optr(x), _optr(xi),
+                                             _optr(ku), ctypes.byref(x_valid), ptr(graph.hub_scratch(K * d)),
                                              stream_of(dev)), "dl_factor_bwd_gather")
         else:
             check(lib().dl_factor_bwd_gather_push(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), K, d,
-                                                  float(beta), one_minus(beta), ptr(dZ), ptr(r), _optr(x),
+                                                  float(beta), one_minus(beta), ptr(dZ), ptr(r),
+                                                  _optr(x) if xi is None else None,
                                                   ctypes.byref(x_valid), ptr(graph.hub_scratch(K * d)),
                                                   peers, len(peers), stream_of(dev)),
                   "dl_factor_bwd_gather_push")
+    if plan is not None:
+        plan["x_valid"] = bool(x_valid.value)
     return bool(x_valid.value)
 
 
@@ -138,14 +174,25 @@ def _sr_scratch(graph: Graph, s):
     return buf
 
 
-def factor_bwd_edges(graph: Graph, Z, G, kstar, w, s, r, beta: float, T: float, dZ, sj=None, x=None):
+def factor_bwd_edges(graph: Graph, Z, G, kstar, w, s, r, beta: float, T: float, dZ, sj=None, plan: dict = None):
     """Pass 2 of the backward: dZ += attention-weight terms (needs r of every neighbour).
-    `x` = the per-entry dots factor_bwd_gather filled (only if it returned True)."""
+    `plan` = the bwd_plan factor_bwd_gather was given."""
     K, d = _check_Z(Z, graph.n_global)
     dev = Z.device
+    valid = plan is not None and plan.get("x_valid")
     with torch.cuda.device(dev):
+        if valid and plan["mode"] == "sym":
+            check(lib().dl_factor_bwd_edges_sym(plan["upper"].ref, plan["lower"].ref, ptr(plan["lmirror"]), ptr(Z), ptr(G),
+                                                ptr(plan["ku"]), ptr(s), ptr(r), ptr(_sr_scratch(graph, s)),
+                                                int(s.shape[0]), ptr(plan["xu"]), ptr(plan["coef"]), K, d,
+                                                one_minus(beta), float(T), ptr(dZ), ptr(graph.hub_scratch(K * d)),
+                                                stream_of(dev)), "dl_factor_bwd_edges_sym")
+            return
+        if plan is not None and plan["mode"] == "sym":
+            raise RuntimeError("pass 1 did not fill the upper-view dots the symmetric pass 2 was planned on")
         check(lib().dl_factor_bwd_edges(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), ptr(r), _optr(sj),
-                                        ptr(_sr_scratch(graph, s)), int(s.shape[0]), _optr(x), K, d,
+                                        ptr(_sr_scratch(graph, s)), int(s.shape[0]),
+                                        ptr(plan["x"]) if valid else None, K, d,
                                         one_minus(beta), float(T), ptr(dZ),
                                         ptr(graph.hub_scratch(K * d)), stream_of(dev)),
               "dl_factor_bwd_edges")
@@ -163,10 +210,11 @@ def factor_bwd(graph: Graph, Z, G, kstar, w, s, beta: float, T: float = 1.0, dZ=
             dZ = torch.zeros_like(Z)
         if r is None:
             r = torch.empty(graph.n_global, K, dtype=torch.float32, device=dev)
-        check(lib().dl_factor_bwd(graph.ref, ptr(Z), ptr(G), ptr(kstar), ptr(w), ptr(s), _optr(sj),
-                                  ptr(_sr_scratch(graph, s)), int(s.shape[0]), ptr(_x_scratch(graph)), K, d,
-                                  float(beta), one_minus(beta), float(T), ptr(dZ), ptr(r),
-                                  ptr(graph.hub_scratch(K * d)), stream_of(dev)), "dl_factor_bwd")
+    plan = bwd_plan(graph, K, d)
+    factor_bwd_gather(graph, Z, G, kstar, w, s, beta, dZ, r, plan=plan)
+    if plan["mode"] == "sym" and not plan["x_valid"]:            # pass 1 took a path without dots: plain pass 2
+        plan = None
+    factor_bwd_edges(graph, Z, G, kstar, w, s, r, beta, T, dZ, sj=sj, plan=plan)
     return dZ, r
 
 

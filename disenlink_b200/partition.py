@@ -407,8 +407,8 @@ class CudaBackend:
     def make_pairs(self, u_loc, v_loc, n_tot):
         return self.ops.PairBatch(u_loc, v_loc, n_tot)
 
-    def entry_scratch(self, g):
-        return self.ops._x_scratch(g)
+    def bwd_plan(self, g, K, d):
+        return self.ops.bwd_plan(g, K, d)
 
     def need_masks(self, g, kstar, halo_off, world, masks):
         from ._lib import check, lib, ptr, stream_of
@@ -440,12 +440,13 @@ class CudaBackend:
         loss, _ = self.ops.link_bce(prob, labels, weights, want_grad=True, dS=dS)
         return loss
 
-    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r, x=None):
-        """-> True when x was filled (backward pass 1)."""
-        return self.ops.factor_bwd_gather(g, Z, G, kstar, w, s, beta, dZ, r, x=x)
+    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r, plan=None):
+        self.ops.factor_bwd_gather(g, Z, G, kstar, w, s, beta, dZ, r, plan=plan)
 
-    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ, sj=None, x=None):
-        self.ops.factor_bwd_edges(g, Z, G, kstar, w, s, r, beta, T, dZ, sj=sj, x=x)
+    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ, sj=None, plan=None):
+        if plan is not None and plan["mode"] == "sym" and not plan["x_valid"]:
+            plan = None
+        self.ops.factor_bwd_edges(g, Z, G, kstar, w, s, r, beta, T, dZ, sj=sj, plan=plan)
 
 
 # --------------------------------------------------------------------------------------------
@@ -510,11 +511,11 @@ class PartitionedLinkStep:
         # the aggregation gathers slices pre-divided by s (scratch = the dH buffer, idle during the forward;
         # own and halo rows alike: s of the halo has been pushed by then); with DL_F_NO_PRESCALE it gathers
         # s[col, kstar] per entry and hands the per-entry copy to pass 2
-        self.prescale = hasattr(be, "entry_scratch") and not (getattr(self.graph, "flags", 0) & 8)
+        self.prescale = hasattr(be, "bwd_plan") and not (getattr(self.graph, "flags", 0) & 8)
         self.sj = None if self.prescale else torch.empty(max(nnz, 1), **f32)
-        # <G[j,k*], Z[i,k*]> per entry, pass 1 -> pass 2 (the graph's per-entry scratch, shared with the
-        # symmetric attention's packed records, which are dead by then)
-        self.x = be.entry_scratch(self.graph) if hasattr(be, "entry_scratch") else None
+        # how pass 1 hands its per-entry dots to pass 2 (and, on one GPU, the symmetric pass 2 with its
+        # coefficient scratch); None: pass 2 gathers everything itself (test backend)
+        self.plan_bwd = be.bwd_plan(self.graph, K, d) if hasattr(be, "bwd_plan") else None
         self.Z = torch.zeros(n_tot, K, d, **f32)
         self.Z_own = self.Z[:n_own]
         self.s = torch.ones(n_tot, K, **f32)
@@ -556,6 +557,7 @@ class PartitionedLinkStep:
         # Write-after-read guard: a peer may still be reading last step's halo rows of Z (backward pass 2
         # is the last reader and no barrier follows it), so nobody overwrites them before everyone is here.
         px.barrier()
+        mark("wait")                 # what the slowest rank of the previous step costs everybody (load imbalance)
         px.push_rows(Z, plan.send_all, plan.recv_all, dst_base=plan.dst_base)
         mark("ag_Z")
         be.edge_attn_fwd(g, Z, self.T, self.kstar, self.w, self.s)
@@ -596,12 +598,12 @@ class PartitionedLinkStep:
             masks = [self.masks[q] for q in range(part.world)] if (d4 and hasattr(be, "need_masks")) else None
             px.push_rows(self.dH, plan.send_all, plan.recv_all, dst_base=plan.dst_base, masks=masks, vec_per_factor=d4)
         mark("ag_dH")
-        xv = be.factor_bwd_gather(g, Z, self.dH, self.kstar, self.w, self.s, self.beta, self.dZ, self.r, x=self.x)
+        be.factor_bwd_gather(g, Z, self.dH, self.kstar, self.w, self.s, self.beta, self.dZ, self.r, plan=self.plan_bwd)
         mark("bwd_gather")
         px.push_rows(self.r, plan.send_all, plan.recv_all, dst_base=plan.dst_base)
         mark("ag_r")
         be.factor_bwd_edges(g, Z, self.dH, self.kstar, self.w, self.s, self.r, self.beta, self.T, self.dZ, self.sj,
-                            x=self.x if xv else None)
+                            plan=self.plan_bwd)
         mark("bwd_edges")
         return self.dZ
 

@@ -35,6 +35,7 @@ extern "C" {
 #define DL_ERANGE (-3)      /* an edge endpoint / pair id is outside [0, N) */
 #define DL_EASYM (-4)       /* adjacency pattern is not symmetric */
 #define DL_EUNSUPPORTED (-5)
+#define DL_EINTERNAL (-6)   /* an internal invariant failed (debug builds only, e.g. -DDL_DEBUG_SINGLE_WRITER) */
 
 #define DL_MAX_K 32         /* kstar is stored in 5 bits of a byte; K-factor count limit */
 #define DL_MAX_D 256        /* per-factor width limit */
@@ -154,6 +155,9 @@ int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float
  *                              the caller reads uptr[N] = nnz_u to size ucol;
  *       call 2: ucol [nnz_u] = its columns, eidx [nnz] = for every entry of the full CSR the position
  *               in the upper view of itself (col >= row) or of its mirror (col < row);
+ *               lcol / lmirror [nnz - nnz_u] (both or neither, may be NULL) = the strictly-lower view
+ *               (row pointers rowptr - uptr): its columns and, per entry, the upper-view position of
+ *               the mirror -- used by the symmetric backward pass 2;
  *               status_out (device int32) = DL_EASYM if some entry has no mirror.
  *       erow = dl_entry_rows of the full CSR.  nnz < 2^31.  ws: dl_sym_index_workspace_bytes(N).
  *   dl_edge_attn_fwd_sym: upper_host = a dl_graph over (uptr, ucol) with its own erow; the factor-per-lane
@@ -164,8 +168,8 @@ int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float
  *       no factor-per-lane instantiation: call dl_edge_attn_fwd instead.  [ref: model.py:56-73] */
 size_t dl_sym_index_workspace_bytes(int64_t N);
 int dl_sym_index(const int64_t* rowptr, const int32_t* col, const int32_t* erow, int64_t N, int64_t nnz,
-                 int64_t* uptr, int32_t* ucol, int32_t* eidx, int32_t* status_out, void* ws, size_t ws_bytes,
-                 dl_stream_t stream);
+                 int64_t* uptr, int32_t* ucol, int32_t* eidx, int32_t* lcol, int32_t* lmirror, int32_t* status_out,
+                 void* ws, size_t ws_bytes, dl_stream_t stream);
 int dl_edge_attn_fwd_sym(const dl_graph* g_host, const dl_graph* upper_host, const int32_t* eidx, const float* Z,
                          int K, int d, float T, uint8_t* kstar, float* w, float* s, float* hub_ws,
                          float* kw_scratch, dl_stream_t stream);
@@ -203,11 +207,29 @@ int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const 
  * gathers and the row's own Z[i]: it leaves x[e] = <G[j,kstar], Z[i,kstar]> there (canonical dot
  * order) and pass 2 reads those 4 bytes instead of gathering the 64-byte slice a second time.
  * x_valid_out (host int, may be NULL) is set to 1 when the pass-1 path taken filled x (the
- * streaming path), else 0; dl_factor_bwd_edges must only be given an x that was filled. */
+ * streaming path), else 0; dl_factor_bwd_edges must only be given an x that was filled.
+ * x_index (may be NULL): the eidx of dl_sym_index.  When given, only the entries with col >= row are
+ * written, at x[x_index[e]] (upper-view order, nnz_u floats), and ku_out [nnz_u] (may be NULL) receives their
+ * kstar in the same order -- the layout dl_factor_bwd_edges_sym reads. */
 int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
                          const uint8_t* kstar, const float* w, const float* s, int K, int d,
                          float beta, float one_minus_beta, float* dZ, float* r, float* x,
-                         int* x_valid_out, float* hub_ws, dl_stream_t stream);
+                         const int32_t* x_index, uint8_t* ku_out, int* x_valid_out, float* hub_ws,
+                         dl_stream_t stream);
+/* Pass 2 evaluating every undirected edge once (csrc/bwd_sym.cu): the coefficients
+ * coef_e[kap] = dwsum_e w_e / T ((kap == kstar_e) - a_e[kap]) are the same numbers for (i,j) and (j,i), so the
+ * dots, exponentials, softmax and (s, r) gathers run on the upper-triangle view only (phase A, which stores
+ * coef [nnz_u, K] in coef_scratch) and the strictly-lower view gathers Z[j] and its mirror's coefficients
+ * (phase B).  upper_host / lower_host / lmirror: dl_sym_index views (each with its own erow); ku, xu: kstar and
+ * <G[j,k*], Z[i,k*]> in upper-view order (dl_factor_bwd_gather with x_index); sr_scratch: 2 n_nodes K floats;
+ * coef_scratch: nnz_u K floats; hub_ws: dl_hub_scratch_floats(full graph, K*d) floats.  dZ is accumulated
+ * into.  Equal to dl_factor_bwd_edges up to fp32 rounding (the two directions of an edge associate dwsum and
+ * the row sums differently).  DL_EUNSUPPORTED when (K, d) has no factor-per-lane instantiation. */
+int dl_factor_bwd_edges_sym_supported(int K, int d);     /* 1 when (K, d) has the kernels, else 0 */
+int dl_factor_bwd_edges_sym(const dl_graph* upper_host, const dl_graph* lower_host, const int32_t* lmirror,
+                            const float* Z, const float* G, const uint8_t* ku, const float* s, const float* r,
+                            float* sr_scratch, int64_t n_nodes, const float* xu, float* coef_scratch, int K, int d,
+                            float one_minus_beta, float T, float* dZ, float* hub_ws, dl_stream_t stream);
 int dl_factor_bwd_edges(const dl_graph* g_host, const float* Z, const float* G,
                         const uint8_t* kstar, const float* w, const float* s, const float* r,
                         const float* sj, float* sr_scratch, int64_t n_nodes, const float* x, int K,

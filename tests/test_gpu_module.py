@@ -342,3 +342,104 @@ def test_fused_exchange_kernels_write_every_peer(K, d):
     assert torch.equal(dZ, dZ_ref) and torch.equal(dH, dH_ref)
     for p in peers:
         assert torch.equal(p, dH)
+
+
+def test_graph_cache_identity_and_sparse_adj():
+    """One module, several adjacencies (train vs eval, a new split): the cached CSR must follow the tensor
+    OBJECT, not its address (the allocator reuses a freed adjacency's address); sparse COO / CSR
+    adjacencies are accepted."""
+    g = load_golden("module_small")
+    n = int(g["N"])
+    m = build(g)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    adj1 = dense_adj_sym(g["src"], g["dst"], n).to(DEV)
+    H1, _ = m(x, adj1)
+    ptr1 = adj1.data_ptr()
+    del adj1
+    adj2 = dense_adj_sym(g["src"][:60], g["dst"][:60], n).to(DEV)      # usually lands at the same address
+    H2, _ = m(x, adj2)
+    from disenlink_b200.model import Disentangle
+    fresh = Disentangle(int(g["F"]), int(g["nhid"]), int(g["d"]), nfactor=int(g["K"]), beta=float(g["beta"]), t=1)
+    fresh.load_state_dict(m.state_dict())
+    H2_ref, _ = fresh.to(DEV)(x, adj2)
+    assert torch.equal(H2, H2_ref), f"stale graph served (address reused: {adj2.data_ptr() == ptr1})"
+    assert not torch.equal(H1, H2)
+    # in-place edit of the same tensor bumps its version: the CSR is rebuilt
+    adj2[0, :] = 0
+    adj2[:, 0] = 0
+    H3, _ = m(x, adj2)
+    assert torch.equal(H3[0], m.beta * m.project(x)[0].reshape(-1).detach()) or torch.allclose(
+        H3[0], m.beta * m.project(x)[0].reshape(-1).detach(), rtol=1e-6, atol=1e-7)
+    # sparse layouts
+    adj_d = dense_adj_sym(g["src"], g["dst"], n).to(DEV)
+    Hd, sc = m(x, adj_d)
+    for sp in (adj_d.to_sparse(), adj_d.to_sparse_csr()):
+        Hs, scorer = m(x, sp)
+        assert torch.equal(Hs, Hd)
+
+
+@pytest.mark.parametrize("row_floats,masked", [(8, False), (128, False), (128, True), (160, True)])
+def test_push_rows_kernel(row_floats, masked):
+    """dl_push_rows / dl_need_masks: indexed rows (and routed slices) land where the descriptor says,
+    everything else in the destination stays untouched (peers emulated by local buffers)."""
+    import ctypes
+    from disenlink_b200._lib import DlPushDesc, check, lib, stream_of
+    rng = np.random.default_rng(row_floats + masked)
+    n_src, n_dst = 5000, 7000
+    src = torch.from_numpy(rng.standard_normal((n_src, row_floats)).astype(np.float32)).to(DEV)
+    K = 8 if row_floats % 8 == 0 else 5
+    vpf = row_floats // K // 4 if masked else 0
+    peers, descs_keep = [], []
+    descs = (DlPushDesc * 3)()
+    expect = []
+    for q in range(3):
+        n = [1200, 0, 3000][q]
+        sidx = torch.from_numpy(rng.choice(n_src, n, replace=False).astype(np.int32)).to(DEV)
+        contiguous = q == 0
+        didx = None if contiguous else torch.from_numpy(rng.choice(n_dst, n, replace=False).astype(np.int32)).to(DEV)
+        mask = torch.from_numpy(rng.integers(0, 2 ** K, n_src).astype(np.int32)).to(DEV) if masked else None
+        dst = torch.full((n_dst, row_floats), -7.0, device=DEV)
+        base = 100 if contiguous else 0
+        exp = dst.clone()
+        rows = (torch.arange(n, device=DEV) + base) if contiguous else didx.long()
+        val = src[sidx.long()]
+        if masked:
+            keep = ((mask[sidx.long()].long()[:, None] >> torch.arange(K, device=DEV)[None, :]) & 1).bool()
+            keep = keep.repeat_interleave(row_floats // K, dim=1)
+            val = torch.where(keep, val, exp[rows])
+        exp[rows] = val
+        expect.append(exp)
+        peers.append(dst)
+        descs_keep.append((sidx, didx, mask))
+        descs[q].dst = dst.data_ptr() + base * row_floats * 4
+        descs[q].src_idx = sidx.data_ptr()
+        descs[q].dst_idx = didx.data_ptr() if didx is not None else None
+        descs[q].mask = mask.data_ptr() if mask is not None else None
+        descs[q].n = n
+    check(lib().dl_push_rows(src.data_ptr(), row_floats * 4, vpf, descs, 3, stream_of(torch.device(DEV))), "dl_push_rows")
+    torch.cuda.synchronize()
+    for dst, exp in zip(peers, expect):
+        assert torch.equal(dst, exp)
+
+
+def test_need_masks_kernel():
+    """masks[p][row] = OR of (1 << kstar) over the row's entries whose column lies in owner p's halo block."""
+    from disenlink_b200._lib import check, lib, ptr, stream_of
+    from disenlink_b200.graph import Graph
+    rng = np.random.default_rng(4)
+    n_own, n_tot, K, world = 3000, 9000, 8, 4
+    deg = rng.integers(0, 40, n_own)
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    col = np.concatenate([np.sort(rng.choice(n_tot, d_, replace=False)) for d_ in deg]).astype(np.int32)
+    kstar = rng.integers(0, K, col.size).astype(np.uint8)
+    halo_off = np.array([n_own, n_own + 1500, n_own + 1500, n_own + 4000, n_tot], np.int32)   # block 1 empty (self)
+    g = Graph(torch.from_numpy(rowptr).to(DEV), torch.from_numpy(col).to(DEV), n_own, row_base=0, n_global=n_tot)
+    masks = torch.full((world, n_own), -1, dtype=torch.int32, device=DEV)
+    check(lib().dl_need_masks(g.ref, ptr(torch.from_numpy(kstar).to(DEV)), ptr(torch.from_numpy(halo_off).to(DEV)),
+                              world, ptr(masks), stream_of(torch.device(DEV))), "dl_need_masks")
+    rows = np.repeat(np.arange(n_own), deg)
+    exp = np.zeros((world, n_own), np.int64)
+    part = np.searchsorted(halo_off, col, side="right") - 1
+    sel = col >= n_own
+    np.bitwise_or.at(exp, (part[sel], rows[sel]), 1 << kstar[sel].astype(np.int64))
+    assert np.array_equal(masks.cpu().numpy().astype(np.int64), exp)

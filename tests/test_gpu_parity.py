@@ -390,3 +390,68 @@ def test_asymmetric_adjacency_forward_ok_backward_refuses(dl, oracle):
     assert relerr(H.detach().cpu().numpy(), o_H) < ORA_TOL
     with pytest.raises(DlError, match="symmetric"):
         H.sum().backward()
+
+
+def test_backward_pass2_single_writer_invariant(oracle):
+    """The fire-and-forget vector reduction of backward pass 2 (red.global.add.v4.f32) is deterministic
+    only because every row has ONE direct writer per launch.  A -DDL_DEBUG_SINGLE_WRITER build of bwd_fl.cu
+    (tools/build_variant.sh dbgsw bwd_fl.cu -DDL_DEBUG_SINGLE_WRITER) counts the direct writers of every
+    row and fails the call with DL_EINTERNAL on a second one; here it runs over a hub-heavy graph."""
+    import ctypes
+    import os
+    from disenlink_b200 import _lib
+    from disenlink_b200.graph import Graph
+    path = os.path.join(os.path.dirname(_lib.LIB_PATH), "_variants", "lib_dbgsw.so")
+    if not os.path.exists(path):
+        pytest.skip("debug variant not built")
+    dbg = ctypes.CDLL(path)
+    dbg.dl_factor_bwd.restype, dbg.dl_factor_bwd.argtypes = _lib.SIGNATURES["dl_factor_bwd"]
+    import disenlink_b200.ops as ops
+    rng = np.random.default_rng(12)
+    n, K, d = 60000, 8, 16
+    src, dst = random_graph(rng, n, 900000, hubs=((1, 30000), (2, 2049), (3, 2048), (4, 4097)))
+    g = Graph.from_edges(t(src), t(dst), n)
+    Z = t((rng.standard_normal((n, K, d)) * 0.3).astype(np.float32))
+    G = t(rng.standard_normal((n, K, d)).astype(np.float32))
+    kstar, w, s = ops.edge_attn_fwd(g, Z, 1.0)
+    dZ_ref, r_ref = ops.factor_bwd(g, Z, G, kstar, w, s, 0.5, 1.0)
+    dZ, r = torch.zeros_like(Z), torch.empty_like(s)
+    dev = torch.device(DEV)
+    rc = dbg.dl_factor_bwd(g.ref, Z.data_ptr(), G.data_ptr(), kstar.data_ptr(), w.data_ptr(), s.data_ptr(), None,
+                           ops._sr_scratch(g, s).data_ptr(), int(s.shape[0]), ops._x_scratch(g).data_ptr(), K, d,
+                           0.5, 0.5, 1.0, dZ.data_ptr(), r.data_ptr(), g.hub_scratch(K * d).data_ptr(),
+                           _lib.stream_of(dev))
+    assert rc == 0, f"debug build reported rc={rc} (-6 = a row had two direct writers)"
+    assert torch.equal(dZ, dZ_ref) and torch.equal(r, r_ref)
+
+
+@pytest.mark.parametrize("K,d", [(8, 16), (8, 8), (5, 16), (5, 32)])
+def test_symmetric_backward_pass2_equals_two_sided(dl, oracle, K, d):
+    """dl_factor_bwd_edges_sym (every undirected edge evaluated once: coefficients computed on the upper
+    triangle, read back by the lower one) against the two-sided pass 2 and the oracle; (5, 32) has no
+    factor-per-lane kernel and must take the regular path."""
+    ops, Graph = dl
+    from disenlink_b200 import _lib
+    rng = np.random.default_rng(K * 31 + d)
+    n = 40000
+    src, dst = random_graph(rng, n, 300000, hubs=((3, 9000), (77, 2049), (5, 600)))
+    Z = (rng.standard_normal((n, K, d)) * (0.8 / np.sqrt(np.sqrt(d)))).astype(np.float32)
+    G = rng.standard_normal((n, K, d)).astype(np.float32)
+    dZ0 = rng.standard_normal((n, K, d)).astype(np.float32)
+    g = Graph.from_edges(t(src), t(dst), n)
+    g.sym_min_nnz = 0
+    kstar, w, s = ops.edge_attn_fwd(g, t(Z), 1.0)
+    plan = ops.bwd_plan(g, K, d)
+    assert plan["mode"] == ("sym" if (K, d) != (5, 32) else "x")
+    dZ1, r1 = ops.factor_bwd(g, t(Z), t(G), kstar, w, s, 0.5, 1.0, dZ=t(dZ0).clone())
+    dZ1b, _ = ops.factor_bwd(g, t(Z), t(G), kstar, w, s, 0.5, 1.0, dZ=t(dZ0).clone())
+    assert torch.equal(dZ1, dZ1b)                                   # run-to-run bitwise
+    g.flags = _lib.DL_F_NO_SYM
+    assert ops.bwd_plan(g, K, d)["mode"] == "x"
+    dZ2, r2 = ops.factor_bwd(g, t(Z), t(G), kstar, w, s, 0.5, 1.0, dZ=t(dZ0).clone())
+    assert torch.equal(r1, r2)
+    assert relerr(dZ1.cpu().numpy(), dZ2.cpu().numpy()) < 5 * ORA_TOL
+    rowptr, col = oracle.csr_from_edges(src, dst, n)
+    o_k, o_w, o_s = oracle.edge_attn_fwd(rowptr, col, Z, 1.0)
+    o_dZ = oracle.factor_bwd(rowptr, col, Z, G, o_k, o_w, o_s, 0.5, 1.0, dZ_init=dZ0)
+    assert relerr(dZ1.cpu().numpy(), o_dZ) < 5 * ORA_TOL

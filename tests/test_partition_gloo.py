@@ -98,7 +98,7 @@ class OracleBackend:
         dS.copy_(torch.from_numpy(ds))
         return torch.tensor(loss, dtype=torch.float32)
 
-    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r, x=None):
+    def factor_bwd_gather(self, g, Z, G, kstar, w, s, beta, dZ, r, plan=None):
         n = g.n_own
         dz = np.zeros((g.n_tot,) + tuple(dZ.shape[1:]), np.float32)
         dz[:n] = dZ.numpy()
@@ -107,10 +107,9 @@ class OracleBackend:
                                  w[:g.nnz].numpy(), s.numpy(), beta, dz, rr)
         dZ.copy_(torch.from_numpy(dz[:n]))
         r[:n] = torch.from_numpy(rr[:n])
-        return False                                   # x (per-entry dots for pass 2) not filled
 
-    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ, sj=None, x=None):
-        assert x is None
+    def factor_bwd_edges(self, g, Z, G, kstar, w, s, r, beta, T, dZ, sj=None, plan=None):
+        assert plan is None
         n = g.n_own
         dz = np.zeros((g.n_tot,) + tuple(dZ.shape[1:]), np.float32)
         dz[:n] = dZ.numpy()

@@ -8,9 +8,11 @@ import sys
 def main(path, nnz, pairs):
     kernels, cur = {}, None
     for line in open(path):
-        m = re.match(r"----- void <unnamed>::(.*)", line)
+        m = re.match(r"----- (.*)", line)          # every launch header, namespaced or not
         if m:
-            cur = kernels.setdefault(m.group(1).strip(), {})
+            name = re.sub(r"^void ", "", m.group(1).strip())
+            name = re.sub(r"^(<unnamed>|\(anonymous namespace\))::", "", name)
+            cur = kernels.setdefault(name, {})
             continue
         m = re.match(r"\s+(\S+)\s+([\d.]+) (\S+)", line)
         if m and cur is not None:
@@ -23,7 +25,7 @@ def main(path, nnz, pairs):
                 cur["duration_ms_under_ncu"] = float(m.group(2))
     for k in kernels.values():
         k["traffic"] = k.get("dram_bytes_read", 0.0) + k.get("dram_bytes_write", 0.0)
-    phase_of = [("bwd_edges", "k_bwd_edges", nnz), ("attn_fwd", "k_attn_", nnz),
+    phase_of = [("bwd_edges", "k_bwd_edges", nnz), ("attn_fwd", "k_attn_", nnz), ("attn_expand", "k_sym_expand", nnz),
                 ("spmm_fwd", "k_gather_stream<DlMap<8, 16>, 0>", nnz),
                 ("bwd_gather", "k_gather_stream<DlMap<8, 16>, 1>", nnz),
                 ("pair_fwd", "k_pair_score_fwd", pairs), ("pair_bwd", "k_pair_bwd_stream", pairs)]
