@@ -439,6 +439,43 @@ def other_configs(dev, peak):
     return out
 
 
+
+def projection_bench(dev):
+    """The factor projection X W (model.py:16-27,106; the one tensor-core contraction of the path) at the
+    sizes of configs[0] and configs[2]: plain fp32 SGEMM against 3xTF32 on the tensor cores, accuracy
+    against fp64."""
+    import torch
+    from disenlink_b200.model import Disentangle
+    out = {}
+    for name, (n, F_, nhid, d, K) in {"cora_F1433_K3_nhid512_d32": (2708, 1433, 512, 32, 3),
+                                      "pubmed_F500_K8_nhid512_d64": (19717, 500, 512, 64, 8)}.items():
+        torch.manual_seed(0)
+        x = torch.randn(n, F_, device=dev)
+        m = Disentangle(F_, nhid, d, nfactor=K, beta=0.5, t=1).to(dev)
+        m64 = Disentangle(F_, nhid, d, nfactor=K, beta=0.5, t=1).double().to(dev)
+        m64.load_state_dict({k: v.double() for k, v in m.state_dict().items()})
+        with torch.no_grad():
+            ref = m64.project(x.double())
+        flops = 2.0 * n * F_ * K * nhid + 2.0 * n * K * nhid * d
+        rec = {"N": n, "F": F_, "K": K, "nhid": nhid, "d": d, "gflop": round(flops / 1e9, 2)}
+        for mode in ("fp32", "3xtf32"):
+            m.projection = mode
+            with torch.no_grad():
+                for _ in range(3):
+                    Z = m.project(x)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(dev)
+                a.record()
+                for _ in range(10):
+                    Z = m.project(x)
+                b.record()
+                torch.cuda.synchronize(dev)
+            ms = a.elapsed_time(b) / 10
+            rec[mode] = {"ms": round(ms, 4), "TFLOP/s": round(flops / (ms * 1e-3) / 1e12, 2),
+                         "max_rel_err_vs_fp64": float((Z.double() - ref).abs().max() / ref.abs().max())}
+        out[name] = rec
+    return out
+
 # ------------------------------------------------------------------------------------------------
 # N > 1: the partitioned step against a single-GPU step on the same inputs (every rank checks its rows)
 # ------------------------------------------------------------------------------------------------
@@ -665,6 +702,23 @@ def run_native(args):
         gbs = ab[kname] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         kernels[kname] = {"ms": round(ms, 4), "alg_bytes": int(ab[kname]), "GB/s": round(gbs, 1),
                           "frac": round(gbs / peak, 4)}
+    # second bound for the two slice gathers: one random <=128-byte access per entry cannot go faster than the
+    # device's random-access rate, measured by tools/gather_probe.cu (profiles/r02_gather_probe.jsonl)
+    probe_path = os.path.join(ROOT, "profiles", "r02_gather_probe.jsonl")
+    if os.path.exists(probe_path):
+        try:
+            rows = [json.loads(l) for l in open(probe_path) if l.strip()]
+            ceil = max(r["objects_per_s"] for r in rows if r.get("object_bytes") == 64 and r.get("array_gb", 0) > 20
+                       and r.get("method") in ("ldg", "cpasync"))
+            for kname in ("spmm_fwd", "bwd_gather"):
+                if phase_ms[kname] > 0:
+                    rate = nnz_local / (phase_ms[kname] * 1e-3)
+                    kernels[kname]["random_access_bound"] = {
+                        "accesses_per_s": rate, "ceiling": ceil, "frac": round(rate / ceil, 4),
+                        "note": "one random 64-B slice per entry; ceiling = measured random 64-B gathers/s over a "
+                                "25.6 GB array (profiles/r02_gather_probe.jsonl); the phase also streams 8ND bytes"}
+        except Exception:
+            pass
     # SURVEY's P(16D+12) counts four full rows per pair; the pairs are sorted by u and come in groups of
     # 1 + M_NEG sharing u, so z_u / h_u are read once per group: the honest floor is P(8D(1 + 1/(1+m)) + 12)
     pf_ms = phase_ms["pair_fwd"]
@@ -751,6 +805,7 @@ def run_native(args):
             torch.cuda.synchronize(dev)                     # all streams: the last upload included
             return val
 
+        oom = False
         try:
             if nb > 1:
                 upload(0)
@@ -760,13 +815,17 @@ def run_native(args):
             e2e_loss = e2e_run(args.steps, n_warm)
             e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         except torch.cuda.OutOfMemoryError:
+            oom = True                       # handled outside the handler: the traceback pins the failed step's buffers
+        if oom:
             # the second input buffer did not leave room for the step's own buffers: serial staging
+            import gc
+            torch.cuda.synchronize(dev)
             del Zbufs[1:]
             nb = 1
             last.clear()
             Zbufs[0].grad = None
             Zbufs[0].requires_grad_(False)
-            torch.cuda.synchronize(dev)
+            gc.collect()
             torch.cuda.empty_cache()
             e2e_run(max(args.warmup, 1), 0)
             t0 = time.perf_counter()
@@ -856,6 +915,10 @@ def run_native(args):
                   "structured_negative_sampling": {"edges": n_src, "ms": round(ns_ms, 3),
                                                    "edges_per_s": n_src / (ns_ms * 1e-3)}}
         del ei, src64, ns_out
+        try:
+            extras["projection"] = projection_bench(dev)
+        except Exception as ex:                       # a side measurement never costs the headline line
+            extras["projection"] = {"error": repr(ex)[:200]}
 
     if rank != 0:
         if world > 1:

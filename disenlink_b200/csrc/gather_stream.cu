@@ -164,8 +164,12 @@ struct GatherStreamCfg {
   static constexpr size_t SMEM = (size_t)GS_WARPS * WARP_B;
 };
 
+// two CTAs per SM (32 warps): the register allocation must stay at 64 -- without the bound the pass-1
+// instantiation drifted to 106 registers when two kernel parameters were added, i.e. to one CTA per SM and
+// +40 % time (the kernel lives on the number of gathers in flight).  Shapes that need two passes over the
+// factors (NP > 1: wide d) hold twice the accumulators and are left to the compiler.
 template <class M, int MODE>
-__global__ void __launch_bounds__(GS_WARPS * 32)
+__global__ void __launch_bounds__(GS_WARPS * 32, (M::NP == 1) ? 2 : 1)
 k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restrict__ SRC,
                 const unsigned char* __restrict__ kstar, const float* __restrict__ w,
                 const float* __restrict__ s, float beta, float omb, float* __restrict__ OUT,

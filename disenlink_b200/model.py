@@ -96,6 +96,47 @@ class Dec(nn.Module):
 AdjLike = Union[torch.Tensor, Graph]
 
 
+# ---- the factor projection on tensor cores: 3xTF32 -------------------------------------------------
+# The projection X W is the one tensor-core contraction of the path.  Plain TF32 (10-bit mantissa) breaks the
+# 1e-5 parity target, plain fp32 SGEMM leaves the tensor cores idle.  3xTF32 splits both operands into a
+# TF32-exact high part and an fp32 remainder and spends three TF32 tensor-core GEMMs,
+#     a b ~= a_hi b_hi + (a_hi b_lo + a_lo b_hi)        (a_lo b_lo ~ 2^-22 |a||b| is dropped),
+# which keeps fp32-class accuracy (the products are exact, accumulation is fp32).  Library GEMMs (cuBLAS).
+def _tf32_split(a: torch.Tensor):
+    # round to nearest at 10 mantissa bits (what the tensor core keeps), remainder exact in fp32
+    hi = ((a.contiguous().view(torch.int32) + 4096) & -8192).view(torch.float32)
+    return hi, a - hi
+
+
+class _Mm3xTF32(torch.autograd.Function):
+    @staticmethod
+    def _mm(a, b):
+        ah, al = _tf32_split(a)
+        bh, bl = _tf32_split(b)
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            return torch.matmul(ah, bh) + (torch.matmul(ah, bl) + torch.matmul(al, bh))
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return _Mm3xTF32._mm(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous()
+        return _Mm3xTF32._mm(g, b.transpose(-1, -2)), _Mm3xTF32._mm(a.transpose(-1, -2), g)
+
+
+def mm_3xtf32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a @ b (2-D or batched) as three TF32 tensor-core GEMMs with fp32-class accuracy; differentiable."""
+    return _Mm3xTF32.apply(a, b)
+
+
 class _GraphCache:
     """adj is constant across the epochs of a run (main_disentangled.py:141 vs :192), so the CSR
     and its work items are built once per distinct adjacency tensor."""
@@ -245,6 +286,9 @@ class Disentangle(nn.Module):
         self.nfactor = nfactor
         self.beta = beta
         self.dense_limit = dense_limit
+        # "fp32": plain SGEMM (default, bit-compatible with the reference's nn.Linear on the same library);
+        # "3xtf32": three TF32 tensor-core GEMMs per product, fp32-class accuracy (dense CUDA x only)
+        self.projection = "fp32"
 
     def project(self, x: torch.Tensor) -> torch.Tensor:
         """Z [N,K,d] = the K factor MLPs of model.py:106, batched: one [N,F] x [F,K*nhid] GEMM for the
@@ -258,8 +302,11 @@ class Disentangle(nn.Module):
         first = [f.mlp if isinstance(f, Factor) else f.mlp1 for f in self.factors]
         W1 = torch.cat([m.weight for m in first], dim=0)              # [K*nhid, F]
         b1 = torch.cat([m.bias for m in first], dim=0)
+        tc = self.projection == "3xtf32" and x.is_cuda and x.layout == torch.strided
         if x.is_sparse or x.layout == torch.sparse_csr:
             hid = torch.sparse.mm(x, W1.t()) + b1
+        elif tc:
+            hid = mm_3xtf32(x, W1.t()) + b1
         else:
             hid = torch.addmm(b1, x, W1.t())                          # [N, K*nhid]
         N = hid.shape[0]
@@ -268,7 +315,10 @@ class Disentangle(nn.Module):
         hid = F.relu(hid).view(N, K, -1).transpose(0, 1)              # [K, N, nhid]
         W2 = torch.stack([f.mlp2.weight for f in self.factors], dim=0)  # [K, d, nhid]
         b2 = torch.stack([f.mlp2.bias for f in self.factors], dim=0)    # [K, d]
-        Z = torch.baddbmm(b2.unsqueeze(1), hid, W2.transpose(1, 2))   # [K, N, d]
+        if tc:
+            Z = mm_3xtf32(hid.contiguous(), W2.transpose(1, 2)) + b2.unsqueeze(1)
+        else:
+            Z = torch.baddbmm(b2.unsqueeze(1), hid, W2.transpose(1, 2))   # [K, N, d]
         return Z.transpose(0, 1).contiguous()
 
     def embed(self, x: torch.Tensor, adj: AdjLike):

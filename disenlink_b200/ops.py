@@ -123,6 +123,13 @@ def bwd_plan(graph: Graph, K: int, d: int, allow_sym: bool = True) -> dict:
         upper, eidx = graph.sym_view()
         lower, lmirror = graph.sym_lower_view()
         nu = upper.nnz
+        # 4K bytes per undirected edge of scratch (16 GB at nnz = 10^9, K = 8): only when it leaves room for
+        # the rest of the step (a caller that double-buffers 25-GB inputs is better served by the two-sided pass)
+        need = nu * K * 4
+        free_b, _ = torch.cuda.mem_get_info(graph.device)
+        cached = torch.cuda.memory_reserved(graph.device) - torch.cuda.memory_allocated(graph.device)
+        if need + (8 << 30) > free_b + cached and need > (64 << 20):
+            return plan
         try:
             coef = torch.empty(max(nu * K, 1), dtype=torch.float32, device=graph.device)
         except torch.cuda.OutOfMemoryError:
