@@ -76,7 +76,7 @@ SIGNATURES = {
     "dl_hub_items": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "dl_hub_scratch_floats": (_sz, [_GP, _i64]),
     "dl_edge_attn_fwd": (_int, [_GP, _vp, _int, _int, _f, _vp, _vp, _vp, _vp, _vp]),
-    "dl_sym_index_workspace_bytes": (_sz, [_i64]),
+    "dl_sym_index_workspace_bytes": (_sz, [_i64, _i64]),
     "dl_sym_index": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dl_edge_attn_fwd_sym": (_int, [_GP, _GP, _vp, _vp, _int, _int, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dl_factor_spmm_fwd": (_int, [_GP, _vp, _vp, _vp, _vp, _int, _int, _f, _f, _vp, _vp, _vp, _i64, _vp, _vp]),

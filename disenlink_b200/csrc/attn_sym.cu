@@ -6,9 +6,10 @@
 // attn_fl.cu -- which gathers the 512-byte row Z[j] for entry (i,j) AND Z[i] for entry (j,i) -- does
 // every undirected edge twice.  Here each edge is evaluated once:
 //
-//   1. (integer, once per graph)  dl_sym_index: the upper-triangle view of the CSR (entries with
-//      col >= row: rowptr uptr, columns ucol) and, for EVERY entry e of the full CSR, eidx[e] = the
-//      position in the upper view of e itself (col >= row) or of its mirror (col < row).
+//   1. (integer, once per graph)  dl_sym_index: the PRIMARY view of the CSR (of the two entries of an edge
+//      the one whose row has the larger degree, see dl_primary: rowptr uptr, columns ucol) and, for EVERY
+//      entry e of the full CSR, eidx[e] = its position in the primary view, or ~(its mirror's position)
+//      for a secondary entry.  ("upper" / "lower" in names = primary / secondary.)
 //   2. k_attn_fl on the upper view: one row gather per undirected edge, result written as one packed
 //      8-byte record kw[t] = (w, kstar) per upper entry (coalesced).
 //   3. k_sym_expand (this file): a streaming pass over the full CSR that reads kw[eidx[e]] -- sequential
@@ -32,67 +33,75 @@ inline int blocks_for(long long n, int threads = 256) {
   return (int)b;
 }
 
-// fu[r] = first position of row r with col >= r (rows are column-sorted)
-__global__ void k_sym_first_upper(const long long* __restrict__ rowptr, const int* __restrict__ col, long long N,
-                                  long long* __restrict__ fu) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += stride) {
-    long long a = rowptr[r], b = rowptr[r + 1];
-    while (a < b) {
-      const long long mid = (a + b) >> 1;
-      if (col[mid] < r) a = mid + 1; else b = mid;
-    }
-    fu[r] = a;
-  }
+// Which of the two entries (i,j), (j,i) of an undirected edge is evaluated ("primary")?  The one whose ROW
+// has the larger degree (ties: the smaller id; a diagonal entry is its own mirror and primary).  Any
+// antisymmetric rule would do for correctness; this one keeps the long rows long: a hub row keeps nearly all
+// of its entries, the many low-degree rows keep few or none, so the per-row costs of the evaluating kernels
+// (own-row loads, accumulator flush: measured at ~10 entries' worth per row start in backward pass 2) are
+// paid for ~N/4 rows instead of N, where an id-based rule (col >= row) halves every row.
+__device__ __forceinline__ bool dl_primary(const long long* __restrict__ rowptr, int i, int j) {
+  if (i == j) return true;
+  const long long di = __ldg(rowptr + i + 1) - __ldg(rowptr + i), dj = __ldg(rowptr + j + 1) - __ldg(rowptr + j);
+  return di > dj || (di == dj && i < j);
 }
 
-struct UpperCount {
+struct PrimaryFlag {
   const long long* rowptr;
-  const long long* fu;
-  long long N;
-  __device__ __forceinline__ long long operator()(long long i) const { return i < N ? rowptr[i + 1] - fu[i] : 0; }
+  const int* col;
+  const int* erow;
+  long long nnz;
+  __device__ __forceinline__ int operator()(long long e) const {
+    return (e < nnz && dl_primary(rowptr, erow[e], col[e])) ? 1 : 0;
+  }
 };
 
+__global__ void k_sym_uptr(const long long* __restrict__ rowptr, const int* __restrict__ pos, long long N,
+                           long long* __restrict__ uptr) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r <= N; r += stride) uptr[r] = pos[rowptr[r]];
+}
+
+// pos[e] = number of primary entries before e (their position in the primary view)
 __global__ void k_sym_fill(const long long* __restrict__ rowptr, const int* __restrict__ col,
-                           const int* __restrict__ erow, long long nnz, const long long* __restrict__ fu,
-                           const long long* __restrict__ uptr, int* __restrict__ ucol, int* __restrict__ eidx,
+                           const int* __restrict__ erow, long long nnz, const int* __restrict__ pos,
+                           int* __restrict__ ucol, int* __restrict__ eidx,
                            int* __restrict__ lcol, int* __restrict__ lmirror, int* __restrict__ status,
                            unsigned long long* __restrict__ n_diag) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
     const int i = erow[e], j = col[e];
     if (j == i) atomicAdd(n_diag, 1ULL);          // integer count: order independent
-    if (j >= i) {
-      const long long t = uptr[i] + (e - fu[i]);
+    const int t = pos[e];
+    if (pos[e + 1] != t) {                         // primary
       ucol[t] = j;
-      eidx[e] = (int)t;
-    } else {                                       // mirror (j, i) sits in the upper part of row j
-      long long a = fu[j], b = rowptr[j + 1];
+      eidx[e] = t;
+    } else {                                       // secondary: its mirror (j, i) is primary, in row j
+      long long a = rowptr[j], b = rowptr[j + 1];
       const long long b0 = b;
       while (a < b) {
         const long long mid = (a + b) >> 1;
         if (col[mid] < i) a = mid + 1; else b = mid;
       }
-      int t = 0;
-      if (a < b0 && col[a] == i) {
-        t = (int)(uptr[j] + (a - fu[j]));
+      int m = 0;
+      if (a < b0 && col[a] == i && pos[a + 1] != pos[a]) {
+        m = pos[a];
       } else {
         *status = DL_EASYM;
       }
-      eidx[e] = t;
-      if (lcol) {                                  // lower-triangle view: entry e is its (e - uptr[i])-th entry
-        lcol[e - uptr[i]] = j;
-        lmirror[e - uptr[i]] = t;
+      eidx[e] = ~m;                                // negative: "read the record of entry ~eidx in the primary view"
+      if (lcol) {                                  // secondary view: entry e is its (e - pos[e])-th entry
+        lcol[e - t] = j;
+        lmirror[e - t] = m;
       }
     }
   }
 }
 
-// every lower entry found its mirror (k_sym_fill); the pattern is symmetric iff, in addition, no strictly
-// upper entry is left without one: #lower == #upper - #diagonal
-__global__ void k_sym_check(long long nnz, const long long* __restrict__ uptr, long long N,
+// every secondary entry found a primary mirror (k_sym_fill); the pattern is symmetric iff, in addition, no
+// primary off-diagonal entry is left without one: #secondary == #primary - #diagonal
+__global__ void k_sym_check(long long nnz, const int* __restrict__ pos,
                             const unsigned long long* __restrict__ n_diag, int* __restrict__ status) {
-  const long long nu = uptr[N];
+  const long long nu = pos[nnz];
   if (nnz - nu != nu - (long long)*n_diag) *status = DL_EASYM;
 }
 
@@ -141,7 +150,11 @@ k_sym_expand(DlGraphDev g, const int* __restrict__ eidx, const float2* __restric
     m.row = -1; m.idx = 0;
     if (cc >= 0) {
       const long long e = cc * DL_CH + lane;
-      if (e < g.nnz) { m.row = __ldg(g.erow + e); m.idx = __ldg(eidx + e); }
+      if (e < g.nnz) {
+        m.row = __ldg(g.erow + e);
+        const int t = __ldg(eidx + e);
+        m.idx = t < 0 ? ~t : t;             // own record (primary entry) or the mirror's (secondary)
+      }
     }
   };
   auto gather = [&](const Meta& m) {
@@ -210,38 +223,39 @@ k_sym_expand(DlGraphDev g, const int* __restrict__ eidx, const float2* __restric
 
 extern "C" {
 
-size_t dl_sym_index_workspace_bytes(int64_t N) {
-  if (N < 0) return 0;
-  return dlp::align256((size_t)(N + 1) * 8) + dlp::scan_ws_bytes(N + 1, 8) + 256;
+size_t dl_sym_index_workspace_bytes(int64_t N, int64_t nnz) {
+  if (N < 0 || nnz < 0) return 0;
+  return dlp::align256((size_t)(nnz + 2) * 4) + dlp::scan_ws_bytes(nnz + 1, 4) + 256;
 }
 
 int dl_sym_index(const int64_t* rowptr, const int32_t* col, const int32_t* erow, int64_t N, int64_t nnz,
                  int64_t* uptr, int32_t* ucol, int32_t* eidx, int32_t* lcol, int32_t* lmirror, int32_t* status_out,
                  void* ws, size_t ws_bytes, dl_stream_t stream) {
   if (N < 0 || nnz < 0 || !rowptr || !uptr || !ws || (nnz > 0 && (!col || !erow))) return DL_EINVAL;
-  if (ws_bytes < dl_sym_index_workspace_bytes(N)) return DL_EWORKSPACE;
-  if (nnz >= 0x7fffffffLL) return DL_EUNSUPPORTED;       // positions in the upper view are int32
+  if (ws_bytes < dl_sym_index_workspace_bytes(N, nnz)) return DL_EWORKSPACE;
+  if (nnz >= 0x7fffffffLL) return DL_EUNSUPPORTED;       // positions in the primary view are int32
   cudaStream_t st = (cudaStream_t)stream;
-  long long* fu = (long long*)ws;
-  void* scan_ws = (char*)ws + dlp::align256((size_t)(N + 1) * 8);
-  if (N > 0) {
-    k_sym_first_upper<<<blocks_for(N), 256, 0, st>>>((const long long*)rowptr, col, N, fu);
+  int* pos = (int*)ws;
+  void* scan_ws = (char*)ws + dlp::align256((size_t)(nnz + 2) * 4);
+  // pos[e] = number of primary entries before e, e = 0 .. nnz (an exclusive scan of the orientation flags)
+  int rc = dlp::scan<false, int>(PrimaryFlag{(const long long*)rowptr, col, erow, nnz}, dlp::StoreArr<int>{pos}, nnz + 1,
+                                 dlp::OpSum<int>(), 0, scan_ws, st);
+  if (rc) return rc;
+  if (!ucol) {              // call 1: row pointers of the primary view (uptr[N] = number of primary entries)
+    k_sym_uptr<<<blocks_for(N + 1), 256, 0, st>>>((const long long*)rowptr, pos, N, (long long*)uptr);
     DL_LAUNCH_CHECK();
-  }
-  if (!ucol) {              // call 1: row pointers of the upper view (uptr[N] = number of upper entries)
-    return dlp::scan<false, long long>(UpperCount{(const long long*)rowptr, fu, N}, dlp::StoreArr<long long>{(long long*)uptr},
-                                       N + 1, dlp::OpSum<long long>(), 0LL, scan_ws, st);
+    return DL_OK;
   }
   if (!eidx || !status_out || ((lcol == nullptr) != (lmirror == nullptr))) return DL_EINVAL;
   DL_CUDA_TRY(cudaMemsetAsync(status_out, 0, sizeof(int32_t), st));
   unsigned long long* n_diag =
-      (unsigned long long*)((char*)ws + dlp::align256((size_t)(N + 1) * 8) + dlp::scan_ws_bytes(N + 1, 8));
+      (unsigned long long*)((char*)ws + dlp::align256((size_t)(nnz + 2) * 4) + dlp::scan_ws_bytes(nnz + 1, 4));
   DL_CUDA_TRY(cudaMemsetAsync(n_diag, 0, sizeof(unsigned long long), st));
   if (nnz > 0) {
-    k_sym_fill<<<blocks_for(nnz), 256, 0, st>>>((const long long*)rowptr, col, erow, nnz, fu, (const long long*)uptr,
-                                                ucol, eidx, lcol, lmirror, status_out, n_diag);
+    k_sym_fill<<<blocks_for(nnz), 256, 0, st>>>((const long long*)rowptr, col, erow, nnz, pos, ucol, eidx, lcol,
+                                                lmirror, status_out, n_diag);
     DL_LAUNCH_CHECK();
-    k_sym_check<<<1, 1, 0, st>>>(nnz, (const long long*)uptr, N, n_diag, status_out);
+    k_sym_check<<<1, 1, 0, st>>>(nnz, pos, n_diag, status_out);
     DL_LAUNCH_CHECK();
   }
   return DL_OK;

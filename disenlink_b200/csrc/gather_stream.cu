@@ -443,12 +443,15 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
     }
     __syncwarp();
     if (MODE == 1 && want_x && mA.row >= 0) {
-      // xidx (symmetric backward pass 2): only the entries with col >= row are needed, in upper-view order
-      if (xidx == nullptr) xout[c * DL_CH + lane] = xbuf[lane];
-      else if (mA.col >= mA.row) {
+      // xidx (symmetric backward pass 2): only the primary entries (eidx >= 0) are needed, in primary-view order
+      if (xidx == nullptr) {
+        xout[c * DL_CH + lane] = xbuf[lane];
+      } else {
         const int t = __ldg(xidx + c * DL_CH + lane);
-        xout[t] = xbuf[lane];
-        if (ku_out) ku_out[t] = (unsigned char)mA.ks;       // kstar in upper-view order, for phase A
+        if (t >= 0) {
+          xout[t] = xbuf[lane];
+          if (ku_out) ku_out[t] = (unsigned char)mA.ks;     // kstar in primary-view order, for phase A
+        }
       }
     }
     buf ^= 1;

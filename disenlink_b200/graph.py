@@ -199,15 +199,17 @@ class Graph:
             self.rev_index()                   # raises with the library's message
 
     def sym_view(self):
-        """-> (upper-triangle Graph, eidx int32 [nnz]) for the symmetric attention
-        (dl_edge_attn_fwd_sym), or None when the pattern is not symmetric, the graph is
-        row-partitioned or has >= 2^31 entries.  Integer work on the device, done once and cached."""
+        """-> (primary-view Graph, eidx int32 [nnz]) for the symmetric attention (dl_edge_attn_fwd_sym), or
+        None when the pattern is not symmetric, the graph is row-partitioned or has >= 2^31 entries.  Of the
+        two entries of an undirected edge the primary one is the entry whose row has the larger degree (ties:
+        smaller id); eidx[e] = its position in the primary view, or ~(its mirror's position) for a secondary
+        entry.  Integer work on the device, done once and cached."""
         if self._sym is None:
             self._sym = False
             if self.row_base == 0 and self.n_global == self.N and 0 < self.nnz < 2**31 - 1:
                 L, dev, N = lib(), self.device, self.N
                 with torch.cuda.device(dev):
-                    ws_bytes = L.dl_sym_index_workspace_bytes(N)
+                    ws_bytes = L.dl_sym_index_workspace_bytes(N, self.nnz)
                     ws = _ws(ws_bytes, dev)
                     uptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
                     status = torch.zeros(1, dtype=torch.int32, device=dev)

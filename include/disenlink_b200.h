@@ -149,24 +149,27 @@ int dl_edge_attn_fwd(const dl_graph* g_host, const float* Z, int K, int d, float
 
 /* (2s) the same, evaluating every undirected edge ONCE.  q_k(i,j) is symmetric and so are, bit for bit,
  * kstar and w (canonical arithmetic), so for a symmetric adjacency that is not row-partitioned the
- * 512-byte row gather is only needed for the entries with col >= row:
+ * 512-byte row gather is only needed for one entry of every edge -- the PRIMARY one: the entry whose row has
+ * the larger degree (ties: the smaller row id; diagonal entries are primary).  Hub rows thereby keep their
+ * length and most low-degree rows drop out of the evaluating kernels.
  *   dl_sym_index  (integer, once per graph; two calls like dl_hub_items)
- *       call 1 (ucol == NULL): uptr [N+1] (device int64) = row pointers of the upper-triangle view;
+ *       call 1 (ucol == NULL): uptr [N+1] (device int64) = row pointers of the primary view;
  *                              the caller reads uptr[N] = nnz_u to size ucol;
- *       call 2: ucol [nnz_u] = its columns, eidx [nnz] = for every entry of the full CSR the position
- *               in the upper view of itself (col >= row) or of its mirror (col < row);
- *               lcol / lmirror [nnz - nnz_u] (both or neither, may be NULL) = the strictly-lower view
- *               (row pointers rowptr - uptr): its columns and, per entry, the upper-view position of
+ *       call 2: ucol [nnz_u] = its columns, eidx [nnz] = for every entry of the full CSR its position t in
+ *               the primary view (>= 0) or, for a secondary entry, ~t of its mirror (< 0);
+ *               lcol / lmirror [nnz - nnz_u] (both or neither, may be NULL) = the secondary view
+ *               (row pointers rowptr - uptr): its columns and, per entry, the primary-view position of
  *               the mirror -- used by the symmetric backward pass 2;
  *               status_out (device int32) = DL_EASYM if some entry has no mirror.
- *       erow = dl_entry_rows of the full CSR.  nnz < 2^31.  ws: dl_sym_index_workspace_bytes(N).
+ *       erow = dl_entry_rows of the full CSR.  nnz < 2^31.  ws: dl_sym_index_workspace_bytes(N, nnz).
+ *       ("upper" / "lower" in argument names = primary / secondary.)
  *   dl_edge_attn_fwd_sym: upper_host = a dl_graph over (uptr, ucol) with its own erow; the factor-per-lane
  *       attention kernel runs on it and leaves packed (w, kstar) records in kw_scratch (2 * nnz_u floats);
  *       a streaming pass expands them through eidx into kstar / w of the full CSR and makes the row
  *       sums s.  Outputs are identical to dl_edge_attn_fwd (kstar, w bit for bit; s up to the order of
  *       the fp32 row sums).  hub_ws: dl_hub_scratch_floats(g, K) floats.  DL_EUNSUPPORTED when (K, d) has
  *       no factor-per-lane instantiation: call dl_edge_attn_fwd instead.  [ref: model.py:56-73] */
-size_t dl_sym_index_workspace_bytes(int64_t N);
+size_t dl_sym_index_workspace_bytes(int64_t N, int64_t nnz);
 int dl_sym_index(const int64_t* rowptr, const int32_t* col, const int32_t* erow, int64_t N, int64_t nnz,
                  int64_t* uptr, int32_t* ucol, int32_t* eidx, int32_t* lcol, int32_t* lmirror, int32_t* status_out,
                  void* ws, size_t ws_bytes, dl_stream_t stream);
@@ -208,9 +211,9 @@ int dl_factor_bwd(const dl_graph* g_host, const float* Z, const float* G, const 
  * order) and pass 2 reads those 4 bytes instead of gathering the 64-byte slice a second time.
  * x_valid_out (host int, may be NULL) is set to 1 when the pass-1 path taken filled x (the
  * streaming path), else 0; dl_factor_bwd_edges must only be given an x that was filled.
- * x_index (may be NULL): the eidx of dl_sym_index.  When given, only the entries with col >= row are
- * written, at x[x_index[e]] (upper-view order, nnz_u floats), and ku_out [nnz_u] (may be NULL) receives their
- * kstar in the same order -- the layout dl_factor_bwd_edges_sym reads. */
+ * x_index (may be NULL): the eidx of dl_sym_index.  When given, only the primary entries (x_index[e] >= 0)
+ * are written, at x[x_index[e]] (primary-view order, nnz_u floats), and ku_out [nnz_u] (may be NULL) receives
+ * their kstar in the same order -- the layout dl_factor_bwd_edges_sym reads. */
 int dl_factor_bwd_gather(const dl_graph* g_host, const float* Z, const float* G,
                          const uint8_t* kstar, const float* w, const float* s, int K, int d,
                          float beta, float one_minus_beta, float* dZ, float* r, float* x,

@@ -350,14 +350,23 @@ def test_symmetric_attention_equals_two_sided(dl, oracle, K, d):
     upper, eidx = g.sym_view()
     rowptr, col = oracle.csr_from_edges(src, dst, n)
     rows = np.repeat(np.arange(n), np.diff(rowptr))
-    up = col >= rows
+    deg = np.diff(rowptr)
+    # primary entry of an edge: the one whose row has the larger degree (ties: smaller id), diagonal included
+    up = (rows == col) | (deg[rows] > deg[col]) | ((deg[rows] == deg[col]) & (rows < col))
     assert upper.nnz == int(up.sum())
     assert np.array_equal(upper.col.cpu().numpy(), col[up])
     assert np.array_equal(upper.rowptr.cpu().numpy(), np.concatenate([[0], np.cumsum(np.bincount(rows[up], minlength=n))]))
-    # eidx: own position for upper entries, the mirror's for lower ones
-    ukey = rows[up].astype(np.int64) * n + col[up]
-    key = np.where(up, rows.astype(np.int64) * n + col, col.astype(np.int64) * n + rows)
-    assert np.array_equal(eidx.cpu().numpy(), np.searchsorted(ukey, key))
+    # eidx: own position for primary entries, ~(the mirror's position) for secondary ones
+    pos = np.cumsum(up) - up                                   # exclusive count of primaries
+    key = rows.astype(np.int64) * n + col
+    mirror = np.searchsorted(key, col.astype(np.int64) * n + rows)
+    assert np.array_equal(key[mirror], col.astype(np.int64) * n + rows)
+    exp = np.where(up, pos, ~pos[mirror])
+    assert np.array_equal(eidx.cpu().numpy(), exp)
+    lower, lmirror = g.sym_lower_view()
+    assert np.array_equal(lower.col.cpu().numpy(), col[~up])
+    assert np.array_equal(lmirror.cpu().numpy(), pos[mirror][~up])
+    assert np.array_equal(lower.rowptr.cpu().numpy(), rowptr - upper.rowptr.cpu().numpy())
     k1, w1, s1 = (x.clone() for x in ops.edge_attn_fwd(g, t(Z), 1.0))
     g.flags = _lib.DL_F_NO_SYM
     k0, w0, s0 = ops.edge_attn_fwd(g, t(Z), 1.0)
@@ -414,6 +423,7 @@ def test_backward_pass2_single_writer_invariant(oracle):
     Z = t((rng.standard_normal((n, K, d)) * 0.3).astype(np.float32))
     G = t(rng.standard_normal((n, K, d)).astype(np.float32))
     kstar, w, s = ops.edge_attn_fwd(g, Z, 1.0)
+    g.flags = _lib.DL_F_NO_SYM                       # the two-sided pass 2, the path dl_factor_bwd takes
     dZ_ref, r_ref = ops.factor_bwd(g, Z, G, kstar, w, s, 0.5, 1.0)
     dZ, r = torch.zeros_like(Z), torch.empty_like(s)
     dev = torch.device(DEV)
