@@ -35,6 +35,9 @@ WORKLOADS = {
     # BASELINE.json configs[4]: synthetic power-law graph 50M nodes / 500M edges, K=8, D=128, 100M pairs
     "c5": dict(N=50_000_000, E=500_000_000, K=8, d=16, P=100_000_000, beta=0.5, T=1.0,
                name="synthetic power-law 50M nodes / 500M directed edges, K=8, d=16 (D=128), 100M link pairs"),
+    # 1.6 x c5: the node arrays alone (4 x 41 GB) exceed one B200 -- only runs node-partitioned (--gpus 8)
+    "c6": dict(N=80_000_000, E=800_000_000, K=8, d=16, P=100_000_000, beta=0.5, T=1.0,
+               name="synthetic power-law 80M nodes / 800M directed edges, K=8, d=16 (does not fit one GPU)"),
     # BASELINE.json configs[3] scale: snap-patents-sized synthetic
     "c4": dict(N=2_923_922, E=13_975_788, K=8, d=16, P=16_000_000, beta=0.5, T=1.0,
                name="snap-patents-scale synthetic 2.92M nodes / 13.98M directed edges, K=8, d=16"),
