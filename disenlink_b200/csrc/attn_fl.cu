@@ -110,7 +110,7 @@ k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __r
   const unsigned myblk = (unsigned)(kap * C4 * 16) | ((unsigned)C::key(kap) << 4);
 
   DlChunkStream cs;
-  cs.init(g.nnz, (long long)gridDim.x * C::NW);
+  cs.init(g.nnz, (long long)gridDim.x * C::NW, g.range_shift);
 
   // unconditional loads from a clamped index (a select against a default right after the load would
   // make the warp wait for it at once); validity is applied in finish_meta, half a chunk later
@@ -200,7 +200,7 @@ k_attn_fl(DlGraphDev g, const float* __restrict__ Z, float T, unsigned char* __r
   while (c >= 0) {
     const long long cn = cs.next(c);
     load_meta(cn, mB);
-    const long long rg = c / DL_RANGE;
+    const long long rg = c >> g.range_shift;
     if (rg != cur_range) {
       if (cur_range >= 0) flush(true);
       cur_range = rg;

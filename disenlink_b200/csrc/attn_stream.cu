@@ -94,7 +94,7 @@ k_attn_stream(DlGraphDev g, const int* __restrict__ erow, const float* __restric
   const unsigned lane_le = 0xffffffffu >> (31 - lane);
 
   DlChunkStream cs;
-  cs.init(g.nnz, (long long)gridDim.x * C::NW);
+  cs.init(g.nnz, (long long)gridDim.x * C::NW, g.range_shift);
   auto load_meta = [&](long long cc, int& r, int& cl) {
     r = -1; cl = 0;
     if (cc >= 0) {

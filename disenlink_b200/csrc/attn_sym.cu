@@ -117,7 +117,7 @@ k_sym_expand(DlGraphDev g, const int* __restrict__ eidx, const float2* __restric
   const long long gw = (long long)blockIdx.x * SX_WARPS + (threadIdx.x >> 5);
   const long long RE = (long long)DL_CH * DL_RANGE;
   DlChunkStream cs;
-  cs.init(g.nnz, (long long)gridDim.x * SX_WARPS);
+  cs.init(g.nnz, (long long)gridDim.x * SX_WARPS, g.range_shift);
 
   // lane k (of every group of KP lanes) accumulates factor k of the current row; with KP = 8 the
   // four lane groups take the entries of a chunk round robin and are summed in a fixed order at the
@@ -175,7 +175,7 @@ k_sym_expand(DlGraphDev g, const int* __restrict__ eidx, const float2* __restric
     const long long cnn = cs.next(cn);
     load_meta(cnn, mC);                 // ids two chunks ahead, records one chunk ahead
     vB = gather(mB);
-    const long long rg = c / DL_RANGE;
+    const long long rg = c >> g.range_shift;
     if (rg != cur_range) {
       if (cur_range >= 0) flush(true);
       cur_range = rg;

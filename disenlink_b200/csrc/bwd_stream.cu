@@ -89,7 +89,7 @@ k_bwd_edges_stream(DlGraphDev g, const float* __restrict__ Z, const float* __res
   const bool unit_T = (T == 1.0f);
 
   DlChunkStream cs;
-  cs.init(g.nnz, (long long)gridDim.x * C::NW);
+  cs.init(g.nnz, (long long)gridDim.x * C::NW, g.range_shift);
 
   auto load_meta = [&](long long cc, BMeta& m) {
     m.row = -1; m.col = 0; m.ks = 255; m.sj = 1.0f; m.rj = 0.0f;
@@ -198,7 +198,7 @@ k_bwd_edges_stream(DlGraphDev g, const float* __restrict__ Z, const float* __res
     load_meta(cnn, mC);       // two chunks ahead
     load_sr(mB);              // s[j,k], r[j,k] of the next chunk (its col / kstar arrived a chunk ago)
 
-    const long long rg = c / DL_RANGE;
+    const long long rg = c >> g.range_shift;
     if (rg != cur_range) {
       if (cur_range >= 0) flush(true);
       cur_range = rg;

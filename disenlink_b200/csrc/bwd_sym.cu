@@ -73,7 +73,7 @@ k_bwd_sym_lower(DlGraphDev g, const int* __restrict__ lmirror, const float* __re
   const unsigned myblk = (unsigned)(kap * C4 * 16) | ((unsigned)C::key(kap) << 4);
 
   DlChunkStream cs;
-  cs.init(g.nnz, (long long)gridDim.x * C::NW);
+  cs.init(g.nnz, (long long)gridDim.x * C::NW, g.range_shift);
 
   // unconditional loads from a clamped index; validity is applied in finish_meta (see bwd_fl.cu)
   auto load_meta = [&](long long cc, LMeta& m) {
@@ -155,7 +155,7 @@ k_bwd_sym_lower(DlGraphDev g, const int* __restrict__ lmirror, const float* __re
   while (c >= 0) {
     const long long cn = cs.next(c);
     load_meta(cn, mB);
-    const long long rg = c / DL_RANGE;
+    const long long rg = c >> g.range_shift;
     if (rg != cur_range) {
       if (cur_range >= 0) flush(true);
       cur_range = rg;

@@ -59,7 +59,20 @@ struct DlGraphDev {
   // from their peer arguments; 0 everywhere else.
   float* peer_out[DL_MAX_PEER_OUT];
   int n_peer_out;
+  // Streaming kernels: the entries are cut into 32-entry chunks and (1 << range_shift) consecutive chunks
+  // form a range owned by one warp.  64 chunks per range on large graphs; fewer on small ones, so that
+  // there are always enough ranges for every warp of the device (a 10^4-entry graph cut into 2048-entry
+  // ranges would leave 5 warps walking them serially at one DRAM / L2 round trip per 4 entries).
+  int range_shift;
 };
+
+// a pure function of nnz: every kernel and every scratch-size query of one graph must agree on it
+static inline __host__ __device__ int dl_range_shift(long long nnz) {
+  const long long n_chunks = (nnz + 31) / 32;
+  int sh = 6;
+  while (sh > 0 && (n_chunks >> sh) < 8192) --sh;
+  return sh;
+}
 
 static inline DlGraphDev dl_graph_dev(const dl_graph* g) {
   DlGraphDev o;
@@ -73,6 +86,7 @@ static inline DlGraphDev dl_graph_dev(const dl_graph* g) {
   o.row_base = g->row_base;
   o.n_peer_out = 0;
   for (int q = 0; q < DL_MAX_PEER_OUT; ++q) o.peer_out[q] = nullptr;
+  o.range_shift = dl_range_shift(g->nnz);
   return o;
 }
 

@@ -27,7 +27,8 @@
 #include "dl_common.cuh"
 
 #define DL_CH 32          // entries per chunk
-#define DL_RANGE 64       // chunks per range (2048 entries)
+#define DL_RANGE (1LL << g.range_shift)   // chunks per range of the graph `g` in scope: 64 (2048 entries) on large
+                                          // graphs, fewer on small ones (dl_range_shift, dl_common.cuh)
 #define DL_HS 4           // entries per ring stage (one sub-block of 4 edges)
 #define DL_QPC (DL_CH / DL_HS)
 #define DL_OWNQ 2         // staged own-row slots per stage (more distinct rows -> plain loads)
@@ -56,17 +57,19 @@ __device__ __forceinline__ float4 dl_lds4(const void* p) { return *reinterpret_c
 // per-warp stream of chunks: ranges gw, gw + GW, ... of DL_RANGE consecutive chunks each
 struct DlChunkStream {
   long long n_chunks, n_ranges, GW;
-  __device__ __forceinline__ void init(long long nnz, long long total_warps) {
+  int sh;                                        // log2(chunks per range)
+  __device__ __forceinline__ void init(long long nnz, long long total_warps, int range_shift) {
+    sh = range_shift;
     n_chunks = (nnz + DL_CH - 1) / DL_CH;
-    n_ranges = (n_chunks + DL_RANGE - 1) / DL_RANGE;
+    n_ranges = (n_chunks + (1LL << sh) - 1) >> sh;
     GW = total_warps;
   }
-  __device__ __forceinline__ long long first(long long gw) const { return gw < n_ranges ? gw * DL_RANGE : -1; }
+  __device__ __forceinline__ long long first(long long gw) const { return gw < n_ranges ? (gw << sh) : -1; }
   __device__ __forceinline__ long long next(long long c) const {
     if (c < 0) return -1;
     const long long c1 = c + 1;
-    if (c1 % DL_RANGE != 0) return c1 < n_chunks ? c1 : -1;
-    const long long rg = c / DL_RANGE + GW;      // first chunk of this warp's next range
-    return rg < n_ranges ? rg * DL_RANGE : -1;
+    if ((c1 & ((1LL << sh) - 1)) != 0) return c1 < n_chunks ? c1 : -1;
+    const long long rg = (c >> sh) + GW;         // first chunk of this warp's next range
+    return rg < n_ranges ? (rg << sh) : -1;
   }
 };

@@ -344,7 +344,7 @@ size_t dl_hub_scratch_floats(const dl_graph* g_host, int64_t width) {
   // hub-segment partials of the row-per-warp kernels, or range carries + chain scratch of the
   // streaming kernels (3 records per 2048-entry range), whichever is larger
   const size_t hub = (size_t)g_host->n_hub_items * (size_t)width;
-  const long long RE = 2048;
+  const long long RE = 32LL << dl_range_shift(g_host->nnz);      // entries per range of the streaming kernels
   const size_t stream = (size_t)((g_host->nnz + RE - 1) / RE) * 3 * (size_t)width;
   return hub > stream ? hub : stream;
 }

@@ -194,7 +194,7 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
   const bool want_x = (MODE == 1) && (L == LP) && xout != nullptr;
 
   DlChunkStream cs;
-  cs.init(g.nnz, (long long)gridDim.x * GS_WARPS);
+  cs.init(g.nnz, (long long)gridDim.x * GS_WARPS, g.range_shift);
 
   struct Meta { int row, col, ks; float wv; };
   auto load_meta = [&](long long cc, Meta& m) {
@@ -357,7 +357,7 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
     __syncwarp();
 
     // range bookkeeping
-    const long long rg = c / DL_RANGE;
+    const long long rg = c >> g.range_shift;
     if (rg != cur_range) {
       if (cur_range >= 0) flush(true);
       cur_range = rg;
@@ -502,7 +502,7 @@ inline int small_grid(long long n_warps_wanted) {
 
 // floats of scratch the streaming gather needs: carries [n_ranges][2][W] + chain scratch [n_ranges][W]
 size_t dl_gather_stream_scratch_floats(long long nnz, int mode, int K, int d) {
-  const long long RE = (long long)DL_CH * DL_RANGE;
+  const long long RE = (long long)DL_CH << dl_range_shift(nnz);
   const long long n_ranges = (nnz + RE - 1) / RE;
   return (size_t)n_ranges * 3 * (size_t)carry_width(mode, K, d);
 }

@@ -70,7 +70,7 @@ k_pair_bwd_stream(DlGraphDev g, const int* __restrict__ inc_pair, const float* _
   const bool unit_T = (T == 1.0f);
 
   DlChunkStream cs;
-  cs.init(g.nnz, (long long)gridDim.x * C::NW);
+  cs.init(g.nnz, (long long)gridDim.x * C::NW, g.range_shift);
   auto load_meta = [&](long long cc, PMeta& m) {
     m.row = -1; m.col = 0; m.pid = 0; m.ds = 0.0f;
     if (cc >= 0) {
@@ -161,7 +161,7 @@ k_pair_bwd_stream(DlGraphDev g, const int* __restrict__ inc_pair, const float* _
     const long long cnn = cs.next(cn);
     load_meta(cnn, mC);
     load_ds(mB);
-    const long long rg = c / DL_RANGE;
+    const long long rg = c >> g.range_shift;
     if (rg != cur_range) {
       if (cur_range >= 0) flush(true);
       cur_range = rg;

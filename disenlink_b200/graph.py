@@ -167,6 +167,12 @@ class Graph:
     def hub_scratch(self, width: int):
         """fp32 scratch for hub-row partials of `width` floats per segment (None if no hubs)."""
         need = int(lib().dl_hub_scratch_floats(self.ref, int(width)))
+        # the symmetric kernels run on the primary / secondary views with this scratch; a view has fewer entries
+        # but may be cut into shorter ranges (dl_range_shift), i.e. into more of them
+        if self._sym:
+            need = max(need, int(lib().dl_hub_scratch_floats(self._sym[0].ref, int(width))))
+        if self._sym_lower:
+            need = max(need, int(lib().dl_hub_scratch_floats(self._sym_lower[0].ref, int(width))))
         if need == 0:
             return None
         if self._hub_ws is None or self._hub_ws.numel() < need:
