@@ -32,6 +32,7 @@
 #endif
 #include "dl_dispatch.cuh"
 #include "dl_stream.cuh"
+#include "dl_fl.cuh"
 
 namespace {
 
@@ -229,10 +230,10 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
   for (int p = 0; p < NP; ++p) acc[p] = dl_zero4();
   int cur_row = -1;
   // row vectors the epilogue needs, loaded when a run STARTS so their latency overlaps the run
-  float4 zpre[NP], gpre[NP], dpre[NP];
+  float4 zpre[NP], gpre[NP];
   float skpre[NP];
 #pragma unroll
-  for (int p = 0; p < NP; ++p) { zpre[p] = gpre[p] = dpre[p] = dl_zero4(); skpre[p] = 1.0f; }
+  for (int p = 0; p < NP; ++p) { zpre[p] = gpre[p] = dl_zero4(); skpre[p] = 1.0f; }
   auto prefetch_row = [&](int row) {
     if (MODE == 2) return;
     const long long node = g.row_base + row;
@@ -241,10 +242,7 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
       if (!M::active(lane, p)) continue;
       const int o = M::offset(lane, p);
       zpre[p] = dl_ldg4(Z + node * D + o);
-      if (MODE == 1) {
-        gpre[p] = dl_ldg4(SRC + node * D + o);
-        dpre[p] = *reinterpret_cast<const float4*>(OUT + node * D + o);
-      }
+      if (MODE == 1) gpre[p] = dl_ldg4(SRC + node * D + o);
     }
     if (MODE == 1) {
 #pragma unroll
@@ -314,14 +312,14 @@ k_gather_stream(DlGraphDev g, const float* __restrict__ Z, const float* __restri
               for (int q = 0; q < g.n_peer_out; ++q) g.peer_out[q][node * K + k] = rv;
             }
             if (act) {
+              // dZ[i] += beta G[i] + T_[i]: this warp is the row's only direct writer in this launch (rows cut by
+              // a range boundary go through the carries), so a fire-and-forget reduction gives the value of
+              // load-add-store in any schedule -- without holding the old dZ chunk in registers for the whole run
               const float4 gi = gpre[p];
-              float4* dp = reinterpret_cast<float4*>(OUT + node * D + o);
-              float4 cur = dpre[p];
-              cur.x = __fadd_rn(cur.x, __fmaf_rn(beta, gi.x, tv.x));
-              cur.y = __fadd_rn(cur.y, __fmaf_rn(beta, gi.y, tv.y));
-              cur.z = __fadd_rn(cur.z, __fmaf_rn(beta, gi.z, tv.z));
-              cur.w = __fadd_rn(cur.w, __fmaf_rn(beta, gi.w, tv.w));
-              *dp = cur;
+              float4 add;
+              add.x = __fmaf_rn(beta, gi.x, tv.x); add.y = __fmaf_rn(beta, gi.y, tv.y);
+              add.z = __fmaf_rn(beta, gi.z, tv.z); add.w = __fmaf_rn(beta, gi.w, tv.w);
+              fl_red_add4(OUT + node * D + o, add);
             }
           }
         }
