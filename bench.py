@@ -523,7 +523,7 @@ def multi_gpu_parity(world, rank, dev, workload="mid"):
     errs = {"s": rel(part_step.s[:n], single.s[lo:hi]), "H": rel(part_step.H[:n], single.H[lo:hi]),
             "r": rel(part_step.r[:n], single.r[lo:hi]), "dZ": rel(part_step.dZ, single.dZ[lo:hi]),
             "dH": rel(part_step.dH[:n], single.dH[lo:hi]),
-            "prob": float((part_step.prob[:P] - single.prob[:P]).abs().max())}
+            "prob": float((part_step.prob[:part_step.P] - single.prob[:part_step.P]).abs().max())}
     vol = part_step.exchange_volume()
     t = torch.tensor([float(ok_int)] + [-e for e in errs.values()], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)

@@ -63,8 +63,10 @@ struct FlCfg {
   static constexpr int EPS = 32 / LPE;                // entries per step
   static constexpr int QPC = DL_CH / EPS;             // steps per chunk
   static constexpr int C4 = d_ / 4;                   // float4 chunks per factor slice
-  static constexpr bool SHAPE_OK = (K_ <= LPE) && (d_ % 4 == 0) && (C4 == 1 || C4 == 2 || C4 == 4) &&
-                                   (2 * K_ <= 32) && (K_ * C4 <= 32);
+  static constexpr bool SHAPE_OK = (K_ <= LPE) && (d_ % 4 == 0) && (C4 == 1 || C4 == 2 || C4 == 4 || C4 == 8) &&
+                                   (2 * K_ <= 32) && (K_ * C4 <= 64);
+  // d = 32: four 32-float slices per lane (own Z, own G, neighbour Z, accumulator) need ~170 registers
+  static constexpr int MAXW = (C4 == 8) ? (FL_MAXW < 12 ? FL_MAXW : 12) : FL_MAXW;
   static constexpr int ROWB = D * 4;
   static constexpr int ROWS = ((ROWB + 127) / 128) * 128;    // staged row stride (128-byte aligned)
   static constexpr int SLB = 128;                             // routed slice slot (d*4 <= 64 used)
@@ -77,7 +79,7 @@ struct FlCfg {
   static constexpr int BUDGET = 226 * 1024;
   static constexpr int NW_RAW = BUDGET / (FL_RING * STAGE_B);
   static constexpr bool OK = SHAPE_OK && NW_RAW >= 4;
-  static constexpr int NW = NW_RAW >= FL_MAXW ? FL_MAXW : (NW_RAW >= 4 ? NW_RAW : 4);
+  static constexpr int NW = NW_RAW >= MAXW ? MAXW : (NW_RAW >= 4 ? NW_RAW : 4);
   static constexpr int THREADS = NW * 32;
   static constexpr size_t SMEM = (size_t)NW * FL_RING * STAGE_B;
   // swizzle key of factor kap: lanes kap, kap' of one 8-lane phase hit the same banks when
@@ -98,6 +100,9 @@ __device__ __forceinline__ float fl_dot(const float4 (&a)[C::C4], const float4 (
   float p[C::C4];
 #pragma unroll
   for (int c = 0; c < C::C4; ++c) p[c] = dl_chunk_dot(a[c], b[c]);
+  if (C::C4 == 8)
+    return __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1 % C::C4]), __fadd_rn(p[2 % C::C4], p[3 % C::C4])),
+                     __fadd_rn(__fadd_rn(p[4 % C::C4], p[5 % C::C4]), __fadd_rn(p[6 % C::C4], p[7 % C::C4])));
   if (C::C4 == 4) return __fadd_rn(__fadd_rn(p[0], p[1]), __fadd_rn(p[2], p[3 % C::C4]));
   if (C::C4 == 2) return __fadd_rn(p[0], p[1 % C::C4]);
   return p[0];
@@ -129,6 +134,16 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
   const int pk = lane / C4, pc = lane % C4;
   const unsigned pdst = (unsigned)(pk * C4 + (pc ^ C::key(pk))) * 16u;
   const bool pact = lane < PIECES;
+  // rows of more than 32 pieces (D > 128): lane t also copies piece t + 32
+  const int pk2 = (lane + 32) / C4;
+  const unsigned pdst2 = (unsigned)(pk2 * C4 + (pc ^ C::key(pk2))) * 16u;
+  const bool pact2 = PIECES > 32 && lane + 32 < PIECES;
+  auto stage_row = [&](unsigned dst, const float* src) {
+    if (pact) fl_cp16(dst + pdst, src + lane * 4);
+    if (PIECES > 32) {
+      if (pact2) fl_cp16(dst + pdst2, src + (lane + 32) * 4);
+    }
+  };
   // compute: my factor's block inside a staged row; chunk c sits at block ^ (c << 4)
   const unsigned myblk = (unsigned)(kap * C4 * 16) | ((unsigned)C::key(kap) << 4);
 
@@ -181,8 +196,7 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
 #pragma unroll
     for (int e = 0; e < EPS; ++e) {
       const long long cc = __shfl_sync(DL_FULL, m.col, q * EPS + e);
-      if (((vq >> e) & 1u) && pact)
-        fl_cp16(st + C::NB_OFF + e * ROWS + pdst, Z + cc * D + lane * 4);
+      if ((vq >> e) & 1u) stage_row(st + C::NB_OFF + e * ROWS, Z + cc * D);
     }
     if (!HAS_X) {   // routed slices G[j, kstar]: lane group e copies the slice of entry e
       const long long cc = __shfl_sync(DL_FULL, m.col, q * EPS + grp);
@@ -198,10 +212,8 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
         starts &= starts - 1;
         const long long node = g.row_base + __shfl_sync(DL_FULL, m.row, q * EPS + pos);
         const unsigned ow = st + C::OWN_OFF + o * OWN_B;
-        if (pact) {
-          fl_cp16(ow + pdst, Z + node * D + lane * 4);
-          fl_cp16(ow + ROWS + pdst, G + node * D + lane * 4);
-        }
+        stage_row(ow, Z + node * D);
+        stage_row(ow + ROWS, G + node * D);
         if (lane < K) fl_cp4(ow + 2 * ROWS + lane * 4, s + node * K + lane);
         else if (lane < 2 * K) fl_cp4(ow + 2 * ROWS + lane * 4, r + node * K + (lane - K));
         ++o;
@@ -455,7 +467,8 @@ __global__ void k_pack_sr(const float* __restrict__ s, const float* __restrict__
 }  // namespace
 
 bool dl_bwd_edges_fl_has(int K, int d) {
-  return (K == 8 && d == 16) || (K == 8 && d == 8) || (K == 5 && d == 16);
+  return (K == 8 && d == 16) || (K == 8 && d == 8) || (K == 5 && d == 16) || (K == 5 && d == 32) ||
+         (K == 3 && d == 32);
 }
 
 int dl_launch_bwd_edges_fl(const DlGraphDev& g, const float* Z, const float* G, const unsigned char* kstar,
@@ -496,6 +509,8 @@ int dl_launch_bwd_sym_upper(const DlGraphDev& gu, const float* Z, const float* G
   FL_CASE(8, 16)
   FL_CASE(8, 8)
   FL_CASE(5, 16)
+  FL_CASE(5, 32)
+  FL_CASE(3, 32)
 #undef FL_CASE
   if (rc != DL_OK) return rc;
   return dl_gather_chain_add(gu, K, d, scratch, dZ, st);

@@ -41,7 +41,8 @@ struct SlCfg {
   static constexpr int STAGE_B = COEF_OFF + 128;            // EPS x 32 bytes of coefficients
   static constexpr int BUDGET = 226 * 1024;
   static constexpr int NW_RAW = BUDGET / (RING * STAGE_B);
-  static constexpr int NW = NW_RAW >= SL_MAXW ? SL_MAXW : (NW_RAW >= 4 ? NW_RAW : 4);
+  static constexpr int MAXW = (C4 == 8) ? (SL_MAXW < 16 ? SL_MAXW : 16) : SL_MAXW;      // d = 32: 2x the registers
+  static constexpr int NW = NW_RAW >= MAXW ? MAXW : (NW_RAW >= 4 ? NW_RAW : 4);
   static constexpr int THREADS = NW * 32;
   static constexpr size_t SMEM = (size_t)NW * RING * STAGE_B;
   __device__ static __forceinline__ int key(int kap) { return (kap / (8 / C4)) & (C4 - 1); }
@@ -70,6 +71,9 @@ k_bwd_sym_lower(DlGraphDev g, const int* __restrict__ lmirror, const float* __re
   const int pk = lane / C4, pc = lane % C4;
   const unsigned pdst = (unsigned)(pk * C4 + (pc ^ C::key(pk))) * 16u;
   const bool pact = lane < PIECES;
+  const int pk2 = (lane + 32) / C4;                      // rows of more than 32 pieces (D > 128)
+  const unsigned pdst2 = (unsigned)(pk2 * C4 + (pc ^ C::key(pk2))) * 16u;
+  const bool pact2 = PIECES > 32 && lane + 32 < PIECES;
   const unsigned myblk = (unsigned)(kap * C4 * 16) | ((unsigned)C::key(kap) << 4);
 
   DlChunkStream cs;
@@ -94,7 +98,12 @@ k_bwd_sym_lower(DlGraphDev g, const int* __restrict__ lmirror, const float* __re
 #pragma unroll
     for (int e = 0; e < EPS; ++e) {
       const long long cc = __shfl_sync(DL_FULL, m.col, q * EPS + e);
-      if (((vq >> e) & 1u) && pact) fl_cp16(st + e * ROWS + pdst, Z + cc * D + lane * 4);
+      if ((vq >> e) & 1u) {
+        if (pact) fl_cp16(st + e * ROWS + pdst, Z + cc * D + lane * 4);
+        if (PIECES > 32) {
+          if (pact2) fl_cp16(st + e * ROWS + pdst2, Z + cc * D + (lane + 32) * 4);
+        }
+      }
     }
     // the mirror's K coefficients: lane (e, kap) copies its own
     const long long mi = __shfl_sync(DL_FULL, m.mir, q * EPS + grp);
@@ -272,6 +281,8 @@ extern "C" int dl_factor_bwd_edges_sym(const dl_graph* upper_host, const dl_grap
   if (K == 8 && d == 16) rc = launch_lower<8, 16>(gl, lmirror, Z, coef_scratch, dZ, hub_ws, st);
   else if (K == 8 && d == 8) rc = launch_lower<8, 8>(gl, lmirror, Z, coef_scratch, dZ, hub_ws, st);
   else if (K == 5 && d == 16) rc = launch_lower<5, 16>(gl, lmirror, Z, coef_scratch, dZ, hub_ws, st);
+  else if (K == 5 && d == 32) rc = launch_lower<5, 32>(gl, lmirror, Z, coef_scratch, dZ, hub_ws, st);
+  else if (K == 3 && d == 32) rc = launch_lower<3, 32>(gl, lmirror, Z, coef_scratch, dZ, hub_ws, st);
   if (rc == -1000) return DL_EUNSUPPORTED;
   if (rc) return rc;
   return dl_gather_chain_add(gl, K, d, hub_ws, dZ, st);

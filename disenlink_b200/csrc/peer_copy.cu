@@ -74,35 +74,49 @@ struct PushTable {
   dl_push_desc d[DL_MAX_PEERS];
 };
 
-// one thread per 16-byte vector of a pushed row; blockIdx.y = peer.  vpf > 0: the row is K factor slices of
-// vpf vectors each and only the slices whose bit is set in mask[source row] are sent.
+// blockIdx.y = peer.  A group of L = 2^lsh lanes (L <= 32, L <= vectors per row) copies one row, 16 bytes per lane
+// and step; a warp therefore moves 32 / L rows at a time and keeps U of them in flight per lane.  No per-vector
+// index arithmetic beyond a shift: the first version divided a 64-bit vector index by the row length for every
+// 16 bytes and was instruction-bound at 270 GB/s on 8 GPUs.
+// vpf > 0: the row is K factor slices of vpf vectors each and only the slices whose bit is set in
+// mask[source row] are sent.
 __global__ void __launch_bounds__(256)
-k_push_rows(const uint4* __restrict__ src, int vpr, int vpf, PushTable tab) {
+k_push_rows(const uint4* __restrict__ src, int vpr, int lsh, int vsh /* log2(vpf), -1: no masks */, PushTable tab) {
   const dl_push_desc d = tab.d[blockIdx.y];
   uint4* __restrict__ dst = reinterpret_cast<uint4*>(d.dst);
-  const long long total = (long long)d.n * vpr;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  constexpr int U = 4;                       // independent 16-byte loads in flight per thread
-  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
-    uint4 v[U];
-    long long di[U];
+  const int L = 1 << lsh;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (L - 1);                          // my first vector of the row
+  const long long rpw = 32 >> lsh;                         // rows per warp and step
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  constexpr int U = 4;
+  for (long long t0 = warp * rpw + (lane >> lsh); t0 < d.n; t0 += nwarps * rpw * U) {
+    long long sr[U], dr[U];
+    unsigned mk[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      di[u] = -1;
-      if (i < total) {
-        const long long t = i / vpr;
-        const int c = (int)(i - t * vpr);
-        const long long sr = d.src_idx ? (long long)__ldg(d.src_idx + t) : t;
-        if (vpf > 0 && d.mask && !((__ldg(d.mask + sr) >> (c / vpf)) & 1u)) continue;
-        const long long dr = d.dst_idx ? (long long)__ldg(d.dst_idx + t) : t;
-        di[u] = dr * vpr + c;
-        v[u] = __ldg(src + sr * vpr + c);
+      const long long t = t0 + u * nwarps * rpw;
+      sr[u] = -1;
+      if (t < d.n) {
+        sr[u] = d.src_idx ? (long long)__ldg(d.src_idx + t) : t;
+        dr[u] = d.dst_idx ? (long long)__ldg(d.dst_idx + t) : t;
+        mk[u] = (vsh >= 0 && d.mask) ? __ldg(d.mask + sr[u]) : 0xffffffffu;
       }
     }
+    for (int c = sub; c < vpr; c += L) {
+      const int k = vsh >= 0 ? (c >> vsh) : 0;
+      uint4 v[U];
+      bool on[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (di[u] >= 0) dst[di[u]] = v[u];
+      for (int u = 0; u < U; ++u) {
+        on[u] = sr[u] >= 0 && ((mk[u] >> k) & 1u);
+        if (on[u]) v[u] = __ldg(src + sr[u] * vpr + c);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (on[u]) dst[dr[u] * vpr + c] = v[u];
+    }
   }
 }
 
@@ -148,12 +162,21 @@ extern "C" int dl_push_rows(const void* src, int64_t row_bytes, int vec_per_fact
   }
   if (most == 0) return DL_OK;
   const int vpr = (int)(row_bytes / 16);
-  long long gx = (most * vpr + 255) / 256;
-  const long long cap = (148LL * 16 + n_peers - 1) / n_peers;
+  int vsh = -1;
+  if (vec_per_factor > 0) {
+    if (vec_per_factor & (vec_per_factor - 1)) return DL_EINVAL;      // slices of 2^n vectors only
+    vsh = 0;
+    while ((1 << vsh) < vec_per_factor) ++vsh;
+  }
+  int lsh = 0;
+  while (lsh < 5 && (2 << lsh) <= vpr) ++lsh;              // lanes per row: largest power of two <= min(32, vpr)
+  const long long rows_per_block = 8LL * (32 >> lsh);
+  long long gx = (most + rows_per_block - 1) / rows_per_block;
+  const long long cap = (148LL * 8 + n_peers - 1) / n_peers;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  k_push_rows<<<dim3((unsigned)gx, (unsigned)n_peers), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, vpr,
-                                                                                      vec_per_factor, tab);
+  k_push_rows<<<dim3((unsigned)gx, (unsigned)n_peers), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, vpr, lsh,
+                                                                                      vsh, tab);
   DL_LAUNCH_CHECK();
   return DL_OK;
 }

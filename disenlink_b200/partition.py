@@ -511,7 +511,10 @@ class PartitionedLinkStep:
         # the aggregation gathers slices pre-divided by s (scratch = the dH buffer, idle during the forward;
         # own and halo rows alike: s of the halo has been pushed by then); with DL_F_NO_PRESCALE it gathers
         # s[col, kstar] per entry and hands the per-entry copy to pass 2
-        self.prescale = hasattr(be, "bwd_plan") and not (getattr(self.graph, "flags", 0) & 8)
+        # -- as long as rescaling every local row (own + halo: 8 D bytes each) costs less than the per-entry gathers
+        # it saves (a rank of an 8-way partition holds ~N halo rows for nnz / 8 entries: there it does not)
+        self.prescale = (hasattr(be, "bwd_plan") and not (getattr(self.graph, "flags", 0) & 8)
+                         and n_tot * 8 <= max(nnz, 1))
         self.sj = None if self.prescale else torch.empty(max(nnz, 1), **f32)
         # how pass 1 hands its per-entry dots to pass 2 (and, on one GPU, the symmetric pass 2 with its
         # coefficient scratch); None: pass 2 gathers everything itself (test backend)
@@ -594,7 +597,7 @@ class PartitionedLinkStep:
         mark("pair_bwd")
         if part.world > 1:
             # only the routed slices G[j, k*] the reader's pass 1 gathers
-            d4 = self.d // 4 if self.d % 4 == 0 else 0
+            d4 = self.d // 4 if (self.d % 4 == 0 and (self.d // 4) & (self.d // 4 - 1) == 0) else 0
             masks = [self.masks[q] for q in range(part.world)] if (d4 and hasattr(be, "need_masks")) else None
             px.push_rows(self.dH, plan.send_all, plan.recv_all, dst_base=plan.dst_base, masks=masks, vec_per_factor=d4)
         mark("ag_dH")

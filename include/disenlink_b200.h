@@ -359,7 +359,7 @@ int dl_pair_score_bwd_push(const dl_graph* inc_host, const int32_t* inc_pair, co
  * dl_push_rows: for every peer q (descs_host[q], host array) and t in [0, n):
  *     dst_q[(dst_idx ? dst_idx[t] : t)] = src[(src_idx ? src_idx[t] : t)]     rows of row_bytes bytes
  * dst = device pointer into the peer's array (mapped with dl_ipc_open), already offset to the block that
- * receives this rank's rows when dst_idx == NULL.  vec_per_factor > 0 and desc.mask != NULL: a row is
+ * receives this rank's rows when dst_idx == NULL.  vec_per_factor > 0 (a power of two) and desc.mask != NULL: a row is
  * K = row_bytes / (16 vec_per_factor) factor slices and only the slices k with bit k of mask[source row]
  * set are sent (the routed slices of dH the peer's backward pass 1 gathers; the others are never read).
  * row_bytes % 16 == 0, pointers 16-byte aligned, n_peers <= 15.  One launch for all peers. */

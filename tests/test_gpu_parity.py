@@ -435,10 +435,10 @@ def test_backward_pass2_single_writer_invariant(oracle):
     assert torch.equal(dZ, dZ_ref) and torch.equal(r, r_ref)
 
 
-@pytest.mark.parametrize("K,d", [(8, 16), (8, 8), (5, 16), (5, 32)])
+@pytest.mark.parametrize("K,d", [(8, 16), (8, 8), (5, 16), (5, 32), (3, 32), (10, 32)])
 def test_symmetric_backward_pass2_equals_two_sided(dl, oracle, K, d):
-    """dl_factor_bwd_edges_sym (every undirected edge evaluated once: coefficients computed on the upper
-    triangle, read back by the lower one) against the two-sided pass 2 and the oracle; (5, 32) has no
+    """dl_factor_bwd_edges_sym (every undirected edge evaluated once: coefficients computed on the primary
+    entries, read back by the secondary ones) against the two-sided pass 2 and the oracle; (10, 32) has no
     factor-per-lane kernel and must take the regular path."""
     ops, Graph = dl
     from disenlink_b200 import _lib
@@ -452,7 +452,7 @@ def test_symmetric_backward_pass2_equals_two_sided(dl, oracle, K, d):
     g.sym_min_nnz = 0
     kstar, w, s = ops.edge_attn_fwd(g, t(Z), 1.0)
     plan = ops.bwd_plan(g, K, d)
-    assert plan["mode"] == ("sym" if (K, d) != (5, 32) else "x")
+    assert plan["mode"] == ("sym" if (K, d) != (10, 32) else "x")
     dZ1, r1 = ops.factor_bwd(g, t(Z), t(G), kstar, w, s, 0.5, 1.0, dZ=t(dZ0).clone())
     dZ1b, _ = ops.factor_bwd(g, t(Z), t(G), kstar, w, s, 0.5, 1.0, dZ=t(dZ0).clone())
     assert torch.equal(dZ1, dZ1b)                                   # run-to-run bitwise
