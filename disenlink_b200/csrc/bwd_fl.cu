@@ -145,7 +145,9 @@ k_bwd_edges_fl(DlGraphDev g, const float* __restrict__ Z, const float* __restric
     }
   };
   // compute: my factor's block inside a staged row; chunk c sits at block ^ (c << 4)
-  const unsigned myblk = (unsigned)(kap * C4 * 16) | ((unsigned)C::key(kap) << 4);
+  // (idle factor lanes, kap >= K, read factor 0's block: their own would lie beyond the row and, for wide rows,
+  // beyond the stage)
+  const unsigned myblk = factive ? ((unsigned)(kap * C4 * 16) | ((unsigned)C::key(kap) << 4)) : 0u;
 
   DlChunkStream cs;
   cs.init(g.nnz, (long long)gridDim.x * C::NW, g.range_shift);

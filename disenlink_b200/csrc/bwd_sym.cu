@@ -74,7 +74,9 @@ k_bwd_sym_lower(DlGraphDev g, const int* __restrict__ lmirror, const float* __re
   const int pk2 = (lane + 32) / C4;                      // rows of more than 32 pieces (D > 128)
   const unsigned pdst2 = (unsigned)(pk2 * C4 + (pc ^ C::key(pk2))) * 16u;
   const bool pact2 = PIECES > 32 && lane + 32 < PIECES;
-  const unsigned myblk = (unsigned)(kap * C4 * 16) | ((unsigned)C::key(kap) << 4);
+  // (idle factor lanes, kap >= K, read factor 0's block: their own would lie beyond the row and, for wide rows,
+  // beyond the stage)
+  const unsigned myblk = factive ? ((unsigned)(kap * C4 * 16) | ((unsigned)C::key(kap) << 4)) : 0u;
 
   DlChunkStream cs;
   cs.init(g.nnz, (long long)gridDim.x * C::NW, g.range_shift);
