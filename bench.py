@@ -497,9 +497,18 @@ def multi_gpu_parity(world, rank, dev, workload="mid"):
         if it == 1:
             part_step.Z_own.mul_(0.9)
         part_step.run()
-    # the single-GPU side runs the same kernels a rank runs (pre-scaled aggregation, packed (s, r)); its
-    # symmetric attention gives bit-identical kstar / w and sums s in the same association
-    single = PartitionedLinkStep(src, dst, N, u, v, lab, wts, K, d, beta, T, world=1, rank=0, device=dev)
+    # the single-GPU side runs the kernel paths a rank runs (two-sided attention and pass 2; the aggregation
+    # pre-scaled or not as the ranks chose), so that what is compared is the partition and the exchange and not two
+    # roundings of the same quantity -- the logits of this workload reach the hundreds and amplify those
+    old_flags = os.environ.get("DL_FLAGS")
+    os.environ["DL_FLAGS"] = "NO_SYM" + ("" if part_step.prescale else ",NO_PRESCALE")
+    try:
+        single = PartitionedLinkStep(src, dst, N, u, v, lab, wts, K, d, beta, T, world=1, rank=0, device=dev)
+    finally:
+        if old_flags is None:
+            del os.environ["DL_FLAGS"]
+        else:
+            os.environ["DL_FLAGS"] = old_flags
     gen_Z(N, K, d, 0, dev, out=single.Z_own)
     single.Z_own.mul_(0.9)
     single.run()

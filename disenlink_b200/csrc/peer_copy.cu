@@ -74,16 +74,17 @@ struct PushTable {
   dl_push_desc d[DL_MAX_PEERS];
 };
 
-// blockIdx.y = peer.  A group of L = 2^lsh lanes (L <= 32, L <= vectors per row) copies one row, 16 bytes per lane
-// and step; a warp therefore moves 32 / L rows at a time and keeps U of them in flight per lane.  No per-vector
-// index arithmetic beyond a shift: the first version divided a 64-bit vector index by the row length for every
-// 16 bytes and was instruction-bound at 270 GB/s on 8 GPUs.
-// vpf > 0: the row is K factor slices of vpf vectors each and only the slices whose bit is set in
+// A group of L = 2^lsh lanes (L <= 32, L <= vectors per row) copies one row, 16 bytes per lane and step; a warp
+// moves 32 / L rows at a time.  The PEERS are the inner loop: a lane group takes row position t of every peer's list
+// in turn, U peers in flight, so that consecutive stores of a warp go to different destinations.  Measured on 4 and 8
+// B200 (tools/a2a_bench.py): a warp that streams to ONE peer sustains ~280-380 GB/s per rank, alternating peers
+// ~690 GB/s -- the rate of the all-gather-style dl_push_slice and above NCCL's all-to-all (614 GB/s).
+// No per-vector index arithmetic beyond a shift (the first version divided a 64-bit vector index for every 16 bytes).
+// vsh >= 0: the row is K factor slices of 2^vsh vectors each and only the slices whose bit is set in
 // mask[source row] are sent.
 __global__ void __launch_bounds__(256)
-k_push_rows(const uint4* __restrict__ src, int vpr, int lsh, int vsh /* log2(vpf), -1: no masks */, PushTable tab) {
-  const dl_push_desc d = tab.d[blockIdx.y];
-  uint4* __restrict__ dst = reinterpret_cast<uint4*>(d.dst);
+k_push_rows(const uint4* __restrict__ src, int vpr, int lsh, int vsh /* log2(vpf), -1: no masks */, int n_peers,
+            long long most, const __grid_constant__ PushTable tab) {
   const int L = 1 << lsh;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (L - 1);                          // my first vector of the row
@@ -91,31 +92,36 @@ k_push_rows(const uint4* __restrict__ src, int vpr, int lsh, int vsh /* log2(vpf
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   constexpr int U = 4;
-  for (long long t0 = warp * rpw + (lane >> lsh); t0 < d.n; t0 += nwarps * rpw * U) {
-    long long sr[U], dr[U];
-    unsigned mk[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long t = t0 + u * nwarps * rpw;
-      sr[u] = -1;
-      if (t < d.n) {
-        sr[u] = d.src_idx ? (long long)__ldg(d.src_idx + t) : t;
-        dr[u] = d.dst_idx ? (long long)__ldg(d.dst_idx + t) : t;
-        mk[u] = (vsh >= 0 && d.mask) ? __ldg(d.mask + sr[u]) : 0xffffffffu;
-      }
-    }
-    for (int c = sub; c < vpr; c += L) {
-      const int k = vsh >= 0 ? (c >> vsh) : 0;
-      uint4 v[U];
-      bool on[U];
+  for (long long t = warp * rpw + (lane >> lsh); t < most; t += nwarps * rpw) {
+    for (int q0 = 0; q0 < n_peers; q0 += U) {
+      long long sr[U], dr[U];
+      unsigned mk[U];
+      uint4* dq[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        on[u] = sr[u] >= 0 && ((mk[u] >> k) & 1u);
-        if (on[u]) v[u] = __ldg(src + sr[u] * vpr + c);
+        const int q = q0 + u;
+        sr[u] = -1;
+        if (q < n_peers && t < tab.d[q].n) {
+          const dl_push_desc& d = tab.d[q];
+          sr[u] = d.src_idx ? (long long)__ldg(d.src_idx + t) : t;
+          dr[u] = d.dst_idx ? (long long)__ldg(d.dst_idx + t) : t;
+          mk[u] = (vsh >= 0 && d.mask) ? __ldg(d.mask + sr[u]) : 0xffffffffu;
+          dq[u] = reinterpret_cast<uint4*>(d.dst);
+        }
       }
+      for (int c = sub; c < vpr; c += L) {
+        const int k = vsh >= 0 ? (c >> vsh) : 0;
+        uint4 v[U];
+        bool on[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (on[u]) dst[dr[u] * vpr + c] = v[u];
+        for (int u = 0; u < U; ++u) {
+          on[u] = sr[u] >= 0 && ((mk[u] >> k) & 1u);
+          if (on[u]) v[u] = __ldg(src + sr[u] * vpr + c);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (on[u]) dq[u][dr[u] * vpr + c] = v[u];
+      }
     }
   }
 }
@@ -172,11 +178,9 @@ extern "C" int dl_push_rows(const void* src, int64_t row_bytes, int vec_per_fact
   while (lsh < 5 && (2 << lsh) <= vpr) ++lsh;              // lanes per row: largest power of two <= min(32, vpr)
   const long long rows_per_block = 8LL * (32 >> lsh);
   long long gx = (most + rows_per_block - 1) / rows_per_block;
-  const long long cap = (148LL * 8 + n_peers - 1) / n_peers;
-  if (gx > cap) gx = cap;
+  if (gx > 148LL * 8) gx = 148LL * 8;
   if (gx < 1) gx = 1;
-  k_push_rows<<<dim3((unsigned)gx, (unsigned)n_peers), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, vpr, lsh,
-                                                                                      vsh, tab);
+  k_push_rows<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, vpr, lsh, vsh, n_peers, most, tab);
   DL_LAUNCH_CHECK();
   return DL_OK;
 }

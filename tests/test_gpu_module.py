@@ -387,7 +387,7 @@ def test_push_rows_kernel(row_floats, masked):
     rng = np.random.default_rng(row_floats + masked)
     n_src, n_dst = 5000, 7000
     src = torch.from_numpy(rng.standard_normal((n_src, row_floats)).astype(np.float32)).to(DEV)
-    K = 8 if row_floats % 8 == 0 else 5
+    K = 5 if row_floats == 160 else 8                      # slices of 2^n vectors: (8, d=16) and (5, d=32)
     vpf = row_floats // K // 4 if masked else 0
     peers, descs_keep = [], []
     descs = (DlPushDesc * 3)()

@@ -25,16 +25,18 @@ def main(path, nnz, pairs):
                 cur["duration_ms_under_ncu"] = float(m.group(2))
     for k in kernels.values():
         k["traffic"] = k.get("dram_bytes_read", 0.0) + k.get("dram_bytes_write", 0.0)
-    phase_of = [("bwd_edges", "k_bwd_edges", nnz), ("attn_fwd", "k_attn_", nnz), ("attn_expand", "k_sym_expand", nnz),
-                ("spmm_fwd", "k_gather_stream<DlMap<8, 16>, 0>", nnz),
-                ("bwd_gather", "k_gather_stream<DlMap<8, 16>, 1>", nnz),
-                ("pair_fwd", "k_pair_score_fwd", pairs), ("pair_bwd", "k_pair_bwd_stream", pairs)]
+    # phase -> the kernels that make it up (the one-sided attention and pass 2 are two launches each)
+    phase_of = [("bwd_edges", ("k_bwd_edges", "k_bwd_sym_lower"), nnz), ("attn_fwd", ("k_attn_", "k_sym_expand"), nnz),
+                ("spmm_fwd", ("k_gather_stream<DlMap<8, 16>, 0>", "k_scale_rows"), nnz),
+                ("bwd_gather", ("k_gather_stream<DlMap<8, 16>, 1>",), nnz),
+                ("pair_fwd", ("k_pair_score_fwd",), pairs), ("pair_bwd", ("k_pair_bwd_stream",), pairs)]
     out = {"workload": f"mid (nnz={nnz}, K=8, d=16, P={pairs}) -- ncu --set full is too slow at c5; bytes scale "
                        "with nnz / P", "source": path, "nnz": nnz, "pairs": pairs, "kernels": kernels}
-    for phase, pat, units in phase_of:
-        for name, k in kernels.items():
-            if name.startswith(pat):
-                out[phase] = {"kernel": name, "traffic_bytes_per_launch": k["traffic"], "per_entry": k["traffic"] / units}
+    for phase, pats, units in phase_of:
+        names = [n for n in kernels if any(n.startswith(p) for p in pats)]
+        if names:
+            tr = sum(kernels[n]["traffic"] for n in names)
+            out[phase] = {"kernels": names, "traffic_bytes_per_launch": tr, "per_entry": tr / units}
     json.dump(out, sys.stdout, indent=1)
 
 
