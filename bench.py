@@ -493,9 +493,13 @@ def multi_gpu_parity(world, rank, dev, workload="mid"):
     part_step = PartitionedLinkStep(src, dst, N, u, v, lab, wts, K, d, beta, T, world=world, rank=rank, device=dev)
     lo, hi = part_step.part.lo, part_step.part.hi
     gen_Z(hi - lo, K, d, 0, dev, row0=lo, out=part_step.Z_own)
-    for it in range(2):                       # two steps, Z changed in between (exchange ordering)
+    # Two steps, Z changed in between (exchange ordering).  The compared step runs on Z / 4: with the
+    # full-scale Z the hub rows of H reach |H| ~ 10^2, and their ABSOLUTE fp32 error (6e-7 relative, from range
+    # cuts that depend on the partition) goes through exp(q) <H_u, H_v> into the scores of the many pairs that
+    # have a hub endpoint -- |d prob| up to 8e-4 at 8 ranks with every forward quantity equal to 6e-7.
+    for it in range(2):
         if it == 1:
-            part_step.Z_own.mul_(0.9)
+            part_step.Z_own.mul_(0.25)
         part_step.run()
     # the single-GPU side runs the kernel paths a rank runs (two-sided attention and pass 2; the aggregation
     # pre-scaled or not as the ranks chose), so that what is compared is the partition and the exchange and not two
@@ -510,7 +514,7 @@ def multi_gpu_parity(world, rank, dev, workload="mid"):
         else:
             os.environ["DL_FLAGS"] = old_flags
     gen_Z(N, K, d, 0, dev, out=single.Z_own)
-    single.Z_own.mul_(0.9)
+    single.Z_own.mul_(0.25)
     single.run()
     torch.cuda.synchronize(dev)
     e0, e1 = int(single.graph.rowptr[lo]), int(single.graph.rowptr[hi])
@@ -544,9 +548,8 @@ def multi_gpu_parity(world, rank, dev, workload="mid"):
            "max_rel_err_vs_single_gpu": {k: -float(x) for k, x in zip(errs.keys(), t[1:].tolist())},
            "loss": float(part_step.loss.item()), "loss_single_gpu": float(single.loss.item()),
            "rank0_rows": vol, "exchange": "NVLink peer push" if part_step.pushed else "torch.distributed p2p"}
-    # bars: forward quantities 1e-5, gradients 5e-5 (relative to the tensor's max-abs); prob = sigmoid(logit) is
-    # compared absolutely and inherits the ABSOLUTE error of logits that reach the hundreds: 2e-4
-    tol = {"s": 1e-5, "H": 1e-5, "r": 5e-5, "dZ": 5e-5, "dH": 5e-5, "prob": 2e-4}
+    # bars: forward quantities 1e-5 (prob: absolute), gradients 5e-5 (relative to the tensor's max-abs)
+    tol = {"s": 1e-5, "H": 1e-5, "r": 5e-5, "dZ": 5e-5, "dH": 5e-5, "prob": 1e-5}
     out["tolerance"] = tol
     out["ok"] = (out["integers_and_routing_bitwise_equal"] and out["kstar_hash"] == out["kstar_hash_single_gpu"]
                  and all(e < tol[k] for k, e in out["max_rel_err_vs_single_gpu"].items()))
