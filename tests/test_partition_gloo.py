@@ -192,14 +192,18 @@ def test_halo_plan_single_rank_is_identity():
     assert torch.equal(plan.to_local(ids), ids)
 
 
-def test_two_rank_gloo_equals_single_process(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_gloo_ranks_equal_single_process(tmp_path, world):
     single, part1 = run_step(1, 0)
     with socket.socket() as sk:
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    outs = [torch.load(os.path.join(tmp_path, f"rank{r}.pt")) for r in range(2)]
-    assert outs[0]["bounds"] == outs[1]["bounds"]
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(os.path.join(tmp_path, f"rank{r}.pt")) for r in range(world)]
+    assert all(o["bounds"] == outs[0]["bounds"] for o in outs)
     assert sum(o["nnz"] for o in outs) == single.graph.nnz
     assert all(0 < o["n_halo"] < part1.n_global for o in outs)          # rank-local storage: own + halo only
     dZ = torch.cat([o["dZ"] for o in outs])
