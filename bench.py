@@ -271,7 +271,8 @@ def dense_reference_leg(device=None):
                 Ho, ao = ours(xg, ag)
             rec["max_abs_diff_link_pred"] = float((ao.cpu() - ar).abs().max())
             rec["max_rel_diff_H"] = float((Ho.cpu() - Hr).abs().max() / Hr.abs().max())
-        out[name] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in rec.items()}
+        out[name] = {k: ((round(v, 4) if abs(v) >= 1e-2 else float(f"{v:.3e}")) if isinstance(v, float) else v)
+                     for k, v in rec.items()}
     return out
 
 
