@@ -144,10 +144,42 @@ k_gather_chain(DlGraphDev g, int mode, int K, int d, const float* __restrict__ c
     if (__ldg(g.rowptr + row) < b * RE) continue;               // the chain started in an earlier range
     const long long last = (__ldg(g.rowptr + row + 1) - 1) / RE;   // range holding the row's last entry
     float* acc = scratch + b * W;
-    for (int x = lane; x < W; x += 32) {
-      float v = carry[(b * 2 + 1) * W + x];                     // tail of the first range
-      for (long long bb = b + 1; bb <= last; ++bb) v = __fadd_rn(v, carry[(bb * 2) * W + x]);
-      acc[x] = v;
+    // every element is summed in range order (the same bits as a plain loop); eight elements per lane and four
+    // ranges per step are in flight, because a hub row of the primary view chains hundreds of ranges and one
+    // dependent load per step made this fix-up 4 % of the step
+    for (int x0 = 0; x0 < W; x0 += 256) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int x = x0 + j * 32 + lane;
+        v[j] = x < W ? carry[(b * 2 + 1) * W + x] : 0.0f;        // tail of the first range
+      }
+      long long bb = b + 1;
+      for (; bb + 3 <= last; bb += 4) {
+        float t[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int x = x0 + j * 32 + lane;
+            t[u][j] = x < W ? carry[((bb + u) * 2) * W + x] : 0.0f;
+          }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __fadd_rn(v[j], t[u][j]);
+      }
+      for (; bb <= last; ++bb)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int x = x0 + j * 32 + lane;
+          if (x < W) v[j] = __fadd_rn(v[j], carry[(bb * 2) * W + x]);
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int x = x0 + j * 32 + lane;
+        if (x < W) acc[x] = v[j];
+      }
     }
     __syncwarp();
     epilogue_flat(g, mode, lane, g.row_base + row, K, d, acc, Z, G, s, beta, omb, OUT, r);
