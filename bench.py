@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- factor-aggregation edges/s (fwd+bwd) and link-pair scores/s on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|mid|tiny] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c6|c4|c4k5|c4k5d64|mid|tiny] [--impl reference]
 
 One "step" = one pass of the hot path over the whole graph and pair batch:
     attention -> aggregation -> pair scoring -> BCE gradient -> decoder backward -> factor backward
@@ -43,6 +43,8 @@ WORKLOADS = {
                name="snap-patents-scale synthetic 2.92M nodes / 13.98M directed edges, K=8, d=16"),
     "c4k5": dict(N=2_923_922, E=13_975_788, K=5, d=32, P=16_000_000, beta=0.5, T=1.0,
                  name="snap-patents-scale synthetic 2.92M nodes / 13.98M directed edges, K=5, d=32"),
+    "c4k5d64": dict(N=2_923_922, E=13_975_788, K=5, d=64, P=16_000_000, beta=0.5, T=1.0,
+                    name="snap-patents-scale synthetic 2.92M nodes / 13.98M directed edges, K=5, d=64"),
     "mid": dict(N=5_000_000, E=50_000_000, K=8, d=16, P=10_000_000, beta=0.5, T=1.0,
                 name="synthetic power-law 5M nodes / 50M directed edges, K=8, d=16 (1/10 of c5)"),
     "tiny": dict(N=200_000, E=2_000_000, K=8, d=16, P=400_000, beta=0.5, T=1.0,
