@@ -25,7 +25,8 @@ what is read, straight into the reader's array over NVLink peer memory (dl_push_
 
 No reduction, no atomics, owner computes; a barrier orders the ranks after each push.  Each row's result
 comes from the same kernel code walking the same column-sorted row as on one GPU, so integers and routing
-are bit-identical to the single-GPU run and floats differ only where a row crosses a 2048-entry range cut.
+are bit-identical to the single-GPU run and floats differ only where a row crosses a range cut of the streaming
+kernels (up to 2048 entries per range; the cuts depend on the local entry count).
 
 Per step:  push Z -> attention -> need-masks, push s -> aggregation -> push H -> pair scores -> gather prob
            -> loss -> decoder backward -> push dH slices -> backward pass 1 -> push r -> backward pass 2

@@ -11,7 +11,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "disenlink_b200", "libdisenlink_b200.so")
 HOT = ["k_attn_fl<8, 16>", "k_sym_expand<8>", "k_gather_stream<DlMap<8, 16>, 0>", "k_gather_stream<DlMap<8, 16>, 1>",
-       "k_bwd_edges_fl<8, 16, true>", "k_pair_score_fwd<DlMap<8, 16>>", "k_pair_bwd_stream<DlMap<8, 16>>",
+       "k_bwd_edges_fl<8, 16, 2>", "k_bwd_edges_fl<8, 16, 1>", "k_bwd_sym_lower<8, 16>", "k_gather_chain",
+       "k_attn_fl<5, 32>", "k_bwd_edges_fl<5, 32, 2>", "k_bwd_sym_lower<5, 32>",
+       "k_pair_score_fwd<DlMap<8, 16>>", "k_pair_bwd_stream<DlMap<8, 16>>",
        "k_scale_rows", "k_push_rows", "k_need_masks"]
 CLASSES = ["LDGSTS", "LDG", "STG", "LDS", "STS", "REDG", "ATOMG", "ATOMS", "RED", "SHFL", "FFMA", "FADD", "FMUL", "MUFU",
            "IMAD", "BRA", "LDL", "STL", "UTMALDG", "UBLKCP", "HMMA", "UTCHMMA"]
