@@ -293,7 +293,10 @@ class PeerExchange:
         if self.world == 1:
             return
         bases = self.peers.get(id(arr)) if self.available else None
-        row_bytes = (arr[0].numel() if arr.dim() > 1 else 1) * arr.element_size()
+        row_elems = 1
+        for n in arr.shape[1:]:
+            row_elems *= int(n)
+        row_bytes = row_elems * arr.element_size()          # (a rank that owns no nodes and reads none has zero rows)
         if bases is not None and row_bytes % 16 == 0:
             from ._lib import DlPushDesc, check, lib, stream_of
             peers = [q for q in range(self.world) if q != self.rank]

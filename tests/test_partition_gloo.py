@@ -129,8 +129,11 @@ def make_inputs(n=203, e=1500, K=3, d=8, P=901, seed=0):
     return src, dst, u, v, lab, wts, Z
 
 
-def run_step(world, rank, group=None):
-    src, dst, u, v, lab, wts, Z = make_inputs()
+CASES = {"default": dict(), "empty_ranks": dict(n=3, e=4, K=2, d=4, P=2, seed=3)}   # 3 nodes over 4 ranks
+
+
+def run_step(world, rank, group=None, case="default"):
+    src, dst, u, v, lab, wts, Z = make_inputs(**CASES[case])
     n, K, d = Z.shape
     step = PartitionedLinkStep(src, dst, n, u, v, lab, wts, K, d, 0.6, 1.0, world=world, rank=rank,
                                group=group, backend=OracleBackend(), device=torch.device("cpu"))
@@ -141,12 +144,12 @@ def run_step(world, rank, group=None):
     return step, part
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, case="default"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        step, part = run_step(world, rank)
+        step, part = run_step(world, rank, case=case)
         n = step.n_own
         torch.save({"dZ": step.dZ.clone(), "H": step.H[:n].clone(), "prob": step.prob.clone(),
                     "loss": step.loss.clone(), "lo": part.lo, "hi": part.hi, "s": step.s[:n].clone(),
@@ -217,3 +220,22 @@ def test_gloo_ranks_equal_single_process(tmp_path, world):
         # the halo rows hold exactly the owners' values
         assert torch.equal(o["Zhalo"], single.Z[o["halo"]])
         assert torch.equal(o["shalo"], single.s[o["halo"]])
+
+
+def test_gloo_ranks_that_own_nothing(tmp_path):
+    """3 nodes over 4 ranks: at least one rank owns no node (zero-row arrays, empty send lists, no pairs to
+    score); the ranks still agree with one process bit for bit."""
+    world = 4
+    single, _ = run_step(1, 0, case="empty_ranks")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_worker, args=(world, port, str(tmp_path), "empty_ranks"), nprocs=world, join=True)
+    outs = [torch.load(os.path.join(tmp_path, f"rank{r}.pt")) for r in range(world)]
+    assert any(o["hi"] == o["lo"] for o in outs)
+    assert torch.equal(torch.cat([o["dZ"] for o in outs]), single.dZ)
+    assert torch.equal(torch.cat([o["H"] for o in outs]), single.H)
+    assert torch.equal(torch.cat([o["r"] for o in outs]), single.r)
+    for o in outs:
+        assert torch.equal(o["prob"][:single.P], single.prob[:single.P])
+        assert torch.equal(o["loss"], single.loss)
