@@ -109,3 +109,37 @@ def test_one_minus_beta_matches_python_double_rounding():
     from oracle import oracle
     for b in (0.5, 0.6, 0.7, 0.8, 0.9, 0.1):
         assert np.float32(one_minus(b)) == oracle.one_minus(b)
+
+
+def test_ctypes_signatures_match_the_header_parameter_lists():
+    """Every declaration of include/disenlink_b200.h against the ctypes signature the host side binds it
+    with: same number of parameters, same class (pointer / int / int64 / float / size) in every position --
+    a drifted binding would pass garbage across the ABI without any error."""
+    from disenlink_b200 import _lib
+    txt = open(os.path.join(ROOT, "include", "disenlink_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = re.sub(r"//[^\n]*", "", txt)
+    decls = re.findall(r"\b(dl_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S)
+    assert len(decls) >= 40
+    scalar = {"int64_t": "i64", "int": "i32", "int32_t": "i32", "float": "f32", "double": "f64", "size_t": "u64",
+              "uint64_t": "u64", "uint32_t": "u32", "dl_stream_t": "ptr", "cudaStream_t": "ptr"}
+
+    def header_kind(p):
+        p = " ".join(p.split())
+        if p in ("", "void"):
+            return None
+        if "*" in p or "[" in p:
+            return "ptr"
+        base = re.sub(r"\b(const|struct)\b", "", p).split()[0]
+        return scalar[base]
+
+    def ctypes_kind(a):
+        if a in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(a, (ctypes._Pointer, ctypes.Array)):
+            return "ptr"
+        return {ctypes.c_int64: "i64", ctypes.c_int: "i32", ctypes.c_float: "f32", ctypes.c_double: "f64",
+                ctypes.c_size_t: "u64", ctypes.c_uint64: "u64", ctypes.c_uint32: "u32"}[a]
+
+    for name, params in decls:
+        want = [k for k in (header_kind(p) for p in params.split(",")) if k is not None]
+        got = [ctypes_kind(a) for a in _lib.SIGNATURES[name][1]]
+        assert want == got, f"{name}: header {want} vs ctypes {got}"
