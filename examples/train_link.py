@@ -119,6 +119,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dataset", default="synthetic")
     ap.add_argument("--root", default="data")
+    ap.add_argument("--sub_dataset", default="Amherst41", help="fb100 school / twitch-e language")
     ap.add_argument("--nfactor", type=int, default=3)
     ap.add_argument("--nhidden", type=int, default=512)
     ap.add_argument("--nembed", type=int, default=32)
@@ -138,6 +139,16 @@ def main():
         args.standardize = False
     elif args.dataset in ("chameleon", "squirrel", "crocodile"):
         x, edge_index, _ = dl_data.read_wikipedia_npz(os.path.join(args.root, args.dataset, "raw", f"{args.dataset}.npz"))
+        args.standardize = True
+    elif args.dataset in ("texas", "wisconsin", "cornell"):                       # main_disentangled.py:69-71,89-94
+        x, edge_index, _ = dl_data.read_webkb(os.path.join(args.root, args.dataset, "raw"))
+        args.standardize = True
+    elif args.dataset == "fb100":                                                   # :61-63,104-108
+        x, edge_index, _ = dl_data.read_fb100(os.path.join(args.root, "facebook100", args.sub_dataset + ".mat"))
+        args.standardize = True
+    elif args.dataset == "twitch-e":                                                # :61-63,104-114 (reversed columns appended)
+        x, edge_index, _ = dl_data.read_twitch(os.path.join(args.root, "twitch", args.sub_dataset), args.sub_dataset)
+        edge_index = torch.cat([edge_index, edge_index.flip(0)], dim=1)
         args.standardize = True
     else:
         x, edge_index, _ = synthetic(seed=args.seed)

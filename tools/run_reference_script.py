@@ -7,7 +7,8 @@ to this repository's implementation (or, with --model reference, to the referenc
 The script (staged byte for byte into baseline/_ref/ by tools/stage_reference.sh) imports
 torch_geometric, torch_sparse-backed loaders and friends at module level (main_disentangled.py:2-17);
 none of them is installed here and none is on the hot path.  This harness registers minimal stand-ins
-in sys.modules for exactly what a `--dataset cora` / `chameleon` run touches:
+in sys.modules for exactly what the datasets with shipped raw files touch (cora, citeseer, chameleon,
+texas / wisconsin / cornell, twitch-e, fb100, year):
 
     torch_geometric.datasets.Planetoid       -> disenlink_b200.data.read_planetoid on data/cora/raw
     torch_geometric.transforms (T.Compose, T.NormalizeFeatures: built at :56, never applied)
@@ -15,7 +16,11 @@ in sys.modules for exactly what a `--dataset cora` / `chameleon` run touches:
                                                 (numpy restatement of PyG's loop on the CPU)
     dataset.WikipediaNetwork                 -> disenlink_b200.data.read_wikipedia_npz (dataset.py:119-124:
                                                 duplicates kept, no to_undirected)
-    other_hetero_datasets.load_nc_dataset    -> raises if called
+    torch_geometric.datasets.WebKB           -> disenlink_b200.data.read_webkb (texas, wisconsin, cornell)
+    other_hetero_datasets.load_nc_dataset    -> read_twitch / read_fb100 behind the NCDataset surface the script
+                                                reads (.graph['edge_index' | 'node_feat' | 'num_nodes'], .label;
+                                                other_hetero_datasets.py:78-154); other names raise
+    torch.load('mini/year<i>.pt')            -> read_pyg_data (a pickled PyG Data object; main_disentangled.py:124)
 
 and then executes the script with runpy, cwd = baseline/_ref, so `./data/` and `data_pre_false/` resolve
 to the staged files.  Nothing in the script is edited.
@@ -66,6 +71,35 @@ def install_stubs(use_ours: bool):
         x, ei, y = dl_data.read_wikipedia_npz(path, coalesce=False)
         return _Dataset(_Data(x, ei, y))
 
+    def webkb(root, name, **kw):
+        x, ei, y = dl_data.read_webkb(os.path.join(root, name, "raw"))
+        return _Dataset(_Data(x, ei, y))
+
+    class _NC:                                                  # NCDataset surface (other_hetero_datasets.py:22-76)
+        def __init__(self, x, ei, y):
+            self.graph = {"edge_index": ei, "edge_feat": None, "node_feat": x, "num_nodes": int(x.shape[0])}
+            self.label = y
+
+    def load_nc_dataset(dataname, sub_dataname=""):
+        if dataname == "twitch-e":
+            if sub_dataname not in ("DE", "ENGB", "ES", "FR", "PTBR", "RU", "TW"):
+                sub_dataname = "DE"                             # other_hetero_datasets.py:84-86
+            return _NC(*dl_data.read_twitch(os.path.join("data", "twitch", sub_dataname), sub_dataname))
+        if dataname == "fb100":
+            if sub_dataname not in ("Penn94", "Amherst41", "Cornell5", "JohnsHopkins55", "Reed98"):
+                sub_dataname = "Penn94"                         # other_hetero_datasets.py:89-91
+            return _NC(*dl_data.read_fb100(os.path.join("data", "facebook100", sub_dataname + ".mat")))
+        raise RuntimeError(f"{dataname}: raw files are not shipped with the reference (not available in this harness)")
+
+    torch_load = torch.load
+
+    def load_pt(f, *a, **kw):
+        if isinstance(f, str) and f.startswith("mini/year"):
+            d = dl_data.read_pyg_data(f)
+            return _Data(d["x"], d["edge_index"], d.get("y", torch.zeros(d["x"].shape[0], dtype=torch.int64)))
+        return torch_load(f, *a, **kw)
+    torch.load = load_pt
+
     def structured_negative_sampling(edge_index, num_nodes=None, contains_neg_self_loops=True):
         if edge_index.is_cuda:
             from disenlink_b200 import ops
@@ -86,11 +120,11 @@ def install_stubs(use_ours: bool):
     structured_negative_sampling.calls = 0
 
     def _unused(*a, **k):
-        raise RuntimeError("not available in this harness (not on the cora / chameleon path)")
+        raise RuntimeError("not available in this harness (its raw files are not shipped with the reference)")
 
     tg = types.ModuleType("torch_geometric")
     tg.datasets = types.ModuleType("torch_geometric.datasets")
-    tg.datasets.Planetoid, tg.datasets.WebKB, tg.datasets.Amazon = planetoid, _unused, _unused
+    tg.datasets.Planetoid, tg.datasets.WebKB, tg.datasets.Amazon = planetoid, webkb, _unused
     tg.transforms = types.ModuleType("torch_geometric.transforms")
     tg.transforms.Compose = lambda ts: ts
     tg.transforms.NormalizeFeatures = lambda: None
@@ -100,7 +134,7 @@ def install_stubs(use_ours: bool):
     ds = types.ModuleType("dataset")
     ds.WikipediaNetwork = wikipedia
     oh = types.ModuleType("other_hetero_datasets")
-    oh.load_nc_dataset = _unused
+    oh.load_nc_dataset = load_nc_dataset
     for m in (tg, tg.datasets, tg.transforms, tg.utils, ds, oh):
         sys.modules[m.__name__] = m
     if use_ours:
