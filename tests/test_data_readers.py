@@ -206,3 +206,14 @@ def test_unmodified_script_runs_over_the_readers_with_the_reference_model(argv):
     assert len(epochs) == 2, out.stdout[-2000:]
     assert all(float(e[1]) == float(e[1]) for e in epochs)
     assert 0.3 < float(re.search(r"test auc: ([0-9.eE+-]+)", out.stdout).group(1)) <= 1.0
+
+
+@staged
+def test_planetoid_citeseer_matches_pyg_canonical_numbers():
+    """CiteSeer has 15 isolated test nodes missing from tx / ty: PyG inserts zero rows for them."""
+    x, ei, y = data.read_planetoid(os.path.join(REF, "data", "citeseer", "raw"), "citeseer")
+    assert tuple(x.shape) == (3327, 3703) and tuple(ei.shape) == (2, 9104) and int(y.max()) == 5
+    assert int((x.sum(1) == 0).sum()) == 15
+    key = ei[0] * 3327 + ei[1]
+    assert bool((key[1:] > key[:-1]).all()) and not bool((ei[0] == ei[1]).any())
+    assert torch.equal(torch.sort(ei[1] * 3327 + ei[0]).values, key)
