@@ -737,7 +737,15 @@ def run_native(args):
     # gather + chain + empty rows (3; + the Z/s streaming pass on one GPU); pair scoring fwd (1); weighted BCE (2);
     # decoder backward = stream + chain + empty nodes (3); backward pass 1 (3); backward pass 2 = (s,r) pack +
     # stream + chain (3)
-    launches_per_step = 18 + (2 if world == 1 else 0)
+    # (checked against the ncu launch list of the same command: profiles/r02_launches_mid.csv, 22 per step)
+    launches_per_step = 18
+    try:
+        g_ = step.graph
+        sym_attn = bool(getattr(g_, "_sym", None)) and g_.nnz >= g_.sym_min_nnz      # + k_sym_expand
+        sym_bwd = bool(step.plan_bwd) and step.plan_bwd.get("mode") == "sym"          # + k_bwd_sym_lower + its chain
+        launches_per_step += int(sym_attn) + int(bool(step.prescale)) + 2 * int(sym_bwd)
+    except Exception:
+        launches_per_step += 2 if world == 1 else 0
     if world > 1 and pushed:                                  # + need-masks, pushes of Z, s, H, dH, r, prob
         launches_per_step += 7
     kernels = {}
