@@ -198,7 +198,7 @@ def test_halo_plan_single_rank_is_identity():
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_gloo_ranks_equal_single_process(tmp_path, world):
     single, part1 = run_step(1, 0)
     with socket.socket() as sk:
