@@ -239,3 +239,60 @@ def test_gloo_ranks_that_own_nothing(tmp_path):
     for o in outs:
         assert torch.equal(o["prob"][:single.P], single.prob[:single.P])
         assert torch.equal(o["loss"], single.loss)
+
+
+# ----------------------------------------------------------------------------------------------
+# the partitioned training loop (examples/train_link_partitioned.py): replicated MLPs, summed gradients
+# ----------------------------------------------------------------------------------------------
+def _trainer_cls():
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "train_link_partitioned.py")
+    spec = importlib.util.spec_from_file_location("_train_link_partitioned", path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.PartitionedLinkTrainer
+
+
+def run_training(world, rank, steps=3):
+    from disenlink_b200.model import Disentangle
+    src, dst, u, v, lab, wts, _ = make_inputs(n=151, e=900, K=3, d=8, P=700, seed=5)
+    n, K, d, F_ = 151, 3, 8, 12
+    x = torch.randn(n, F_, generator=torch.Generator().manual_seed(7))
+    torch.manual_seed(100 + rank)                        # different initial weights per rank: the trainer broadcasts rank 0's
+    model = Disentangle(F_, 16, d, nfactor=K, beta=0.6, t=1)
+    step = PartitionedLinkStep(src, dst, n, u, v, lab, wts, K, d, 0.6, 1.0, world=world, rank=rank,
+                               backend=OracleBackend(), device=torch.device("cpu"))
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    tr = _trainer_cls()(model, x[step.part.lo:step.part.hi], step, opt)
+    losses = [float(tr.train_step()) for _ in range(steps)]
+    return losses, [p.detach().clone() for p in model.parameters()], tr.scores().clone()
+
+
+def _train_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        losses, params, prob = run_training(world, rank)
+        torch.save({"losses": losses, "params": params, "prob": prob}, os.path.join(out_dir, f"train{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_partitioned_training_matches_single_process(tmp_path):
+    """Three Adam steps of the partitioned loop at world 2 against one process: same losses, same weights (up to
+    the summation order of the gradient all-reduce), identical replicas on the ranks."""
+    losses1, params1, prob1 = run_training(1, 0)
+    assert losses1[-1] < losses1[0]
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    outs = [torch.load(os.path.join(tmp_path, f"train{r}.pt")) for r in range(2)]
+    for a, b in zip(outs[0]["params"], outs[1]["params"]):
+        assert torch.equal(a, b)                                              # replicas stay identical
+    for o in outs:
+        assert np.allclose(o["losses"], losses1, rtol=1e-5, atol=0)
+        for a, b in zip(o["params"], params1):
+            assert float((a - b).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1e-6)
+        assert float((o["prob"] - prob1).abs().max()) < 1e-5
