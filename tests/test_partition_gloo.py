@@ -15,7 +15,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from disenlink_b200.partition import HaloPlan, NodePartition, PartitionedLinkStep, owned_entries, pair_shard
+from disenlink_b200.partition import (HaloPlan, NodeOrder, NodePartition, PartitionedLinkStep, locality_partition,
+                                      owned_entries, pair_shard)
 
 
 class _LocalGraph:
@@ -129,14 +130,21 @@ def make_inputs(n=203, e=1500, K=3, d=8, P=901, seed=0):
     return src, dst, u, v, lab, wts, Z
 
 
-CASES = {"default": dict(), "empty_ranks": dict(n=3, e=4, K=2, d=4, P=2, seed=3)}   # 3 nodes over 4 ranks
+CASES = {"default": dict(), "empty_ranks": dict(n=3, e=4, K=2, d=4, P=2, seed=3),   # 3 nodes over 4 ranks
+         "locality": dict()}            # nodes renumbered by locality_partition, explicit split points
+LOCALITY_WORLD = 4
 
 
 def run_step(world, rank, group=None, case="default"):
     src, dst, u, v, lab, wts, Z = make_inputs(**CASES[case])
     n, K, d = Z.shape
+    bounds = None
+    if case == "locality":
+        order, b = locality_partition(src, dst, n, LOCALITY_WORLD)
+        src, dst, u, v, Z = order.relabel(src), order.relabel(dst), order.relabel(u), order.relabel(v), order.rows_to_new(Z)
+        bounds = b if world == LOCALITY_WORLD else None
     step = PartitionedLinkStep(src, dst, n, u, v, lab, wts, K, d, 0.6, 1.0, world=world, rank=rank,
-                               group=group, backend=OracleBackend(), device=torch.device("cpu"))
+                               group=group, backend=OracleBackend(), device=torch.device("cpu"), bounds=bounds)
     part = step.part
     step.Z_own.copy_(Z[part.lo:part.hi])              # each rank only has its own rows before the exchange
     step.run()
@@ -296,3 +304,66 @@ def test_gloo_partitioned_training_matches_single_process(tmp_path):
         for a, b in zip(o["params"], params1):
             assert float((a - b).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1e-6)
         assert float((o["prob"] - prob1).abs().max()) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------
+# locality reorder ("optional locality/degree reorder; keep the permutation and un-permute outputs")
+# ----------------------------------------------------------------------------------------------
+def _halo_stats(src, dst, n, bounds):
+    """-> (halo rows summed over the ranks, share of remote CSR entries, max / mean entries per rank)."""
+    s_, d_ = src.numpy(), dst.numpy()
+    key = np.unique(np.concatenate([s_ * n + d_, d_ * n + s_]))
+    rows, cols = key // n, key % n
+    owner = np.searchsorted(np.asarray(bounds[1:]), np.arange(n), side="right")
+    remote = owner[rows] != owner[cols]
+    halo = np.unique(owner[rows][remote].astype(np.int64) * n + cols[remote]).size
+    load = np.bincount(owner[rows], minlength=len(bounds) - 1)
+    return halo, float(remote.mean()), float(load.max() / load.mean())
+
+
+def test_locality_partition_shrinks_the_halo_of_a_real_graph():
+    """The real Pubmed citation graph (committed fixture), 8 ranks: the nnz-balanced split of the given numbering
+    against locality_partition's renumbering + split points."""
+    gd = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pubmed_graph.npz"))
+    src, dst, n = torch.from_numpy(gd["src"].astype(np.int64)), torch.from_numpy(gd["dst"].astype(np.int64)), int(gd["N"])
+    world = 8
+    base = NodePartition.nnz_balanced(src, dst, n, world, 0).bounds
+    halo0, remote0, bal0 = _halo_stats(src, dst, n, base)
+    order, bounds = locality_partition(src, dst, n, world)
+    assert bounds[0] == 0 and bounds[-1] == n and all(a <= b for a, b in zip(bounds[:-1], bounds[1:]))
+    assert torch.equal(torch.sort(order.new_of_old).values, torch.arange(n))         # a permutation
+    halo1, remote1, bal1 = _halo_stats(order.relabel(src), order.relabel(dst), n, bounds)
+    assert halo1 < 0.5 * halo0 and remote1 < 0.5 * remote0, (halo0, halo1, remote0, remote1)
+    assert bal1 < 1.10
+    order2, bounds2 = locality_partition(src, dst, n, world)                          # deterministic
+    assert bounds2 == bounds and torch.equal(order2.new_of_old, order.new_of_old)
+
+
+def test_renumbered_graph_gives_the_same_result_after_unpermuting():
+    src, dst, u, v, lab, wts, Z = make_inputs()
+    n, K, d = Z.shape
+    plain, _ = run_step(1, 0)
+    order, _ = locality_partition(src, dst, n, LOCALITY_WORLD)
+    moved, _ = run_step(1, 0, case="locality")
+    tol = lambda a, b: float((a - b).abs().max()) <= 2e-5 * max(float(b.abs().max()), 1e-6)  # noqa: E731
+    assert tol(order.rows_to_old(moved.H), plain.H) and tol(order.rows_to_old(moved.dZ), plain.dZ)
+    assert tol(order.rows_to_old(moved.s), plain.s)
+    assert tol(moved.prob[:plain.P], plain.prob[:plain.P]) and tol(moved.loss, plain.loss)
+
+
+def test_gloo_ranks_with_locality_split_points_equal_single_process(tmp_path):
+    world = LOCALITY_WORLD
+    single, _ = run_step(1, 0, case="locality")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_worker, args=(world, port, str(tmp_path), "locality"), nprocs=world, join=True)
+    outs = [torch.load(os.path.join(tmp_path, f"rank{r}.pt")) for r in range(world)]
+    src, dst, *_ = make_inputs()
+    _, bounds = locality_partition(src, dst, single.part.n_global, world)
+    assert outs[0]["bounds"] == bounds
+    assert torch.equal(torch.cat([o["dZ"] for o in outs]), single.dZ)
+    assert torch.equal(torch.cat([o["H"] for o in outs]), single.H)
+    assert torch.equal(torch.cat([o["r"] for o in outs]), single.r)
+    for o in outs:
+        assert torch.equal(o["prob"][:single.P], single.prob[:single.P]) and torch.equal(o["loss"], single.loss)
