@@ -156,7 +156,9 @@ class Graph:
 
     @property
     def flags(self) -> int:
-        """dl_graph.flags: kernel-path switches (_lib.DL_F_*), 0 = the fast paths."""
+        """dl_graph.flags: kernel-path switches (_lib.DL_F_*), 0 = the fast paths.  The primary / secondary
+        views of sym_view() are graphs of their own and keep the flags they were built with (DL_FLAGS at
+        construction); a handle, its scratch buffers and its views serve one stream at a time."""
         return self._flags
 
     @flags.setter
