@@ -284,6 +284,7 @@ def cpu_baseline(K, d, beta, T, steps=2, warmup=1):
     from oracle import oracle
     threads = os.cpu_count() or 1
     oracle.set_num_threads(threads)
+    torch.set_num_threads(threads)     # torchrun exports OMP_NUM_THREADS=1: the (untimed) input generation would crawl
     cs = CPU_SAMPLE
     src, dst = gen_edges(cs["N"], cs["E"], 0, "cpu")
     rowptr, col = oracle.csr_from_edges(src.numpy(), dst.numpy(), cs["N"])
