@@ -61,7 +61,7 @@ def adj_sym_of(src, dst, n):
 def make_case(seed):
     rng = np.random.default_rng(1000 + seed)
     n = int(rng.integers(4, 70))
-    K = int(rng.choice([1, 2, 3, 5, 8, 10]))
+    K = int(rng.choice([1, 2, 3, 5, 8, 10, 20]))          # 20: fb100 Amherst41 in hyperparameters_setting
     d = int(rng.choice([4, 8, 16, 32, 64]))
     beta = float(rng.choice([0.0, 0.3, 0.5, 0.9, 1.0]))
     T = float(rng.choice([1, 1, 2, 3]))                      # --temperature is an int (main_disentangled.py:40)
